@@ -76,8 +76,16 @@ def _attend(q, k, v, bias) -> torch.Tensor:
     return o.transpose(1, 2).reshape(B, T, H * dk)
 
 
-def encoder_forward(w: W, dims: T5Dims, input_ids: torch.Tensor, attention_mask: torch.Tensor) -> torch.Tensor:
-    """HF T5 encoder stack: [B,S] ids -> [B,S,d] (final layer norm applied)."""
+def _lin(x: torch.Tensor, weight: torch.Tensor) -> torch.Tensor:
+    """nn.Linear without bias: x @ W^T in fp32."""
+    return x @ weight.t()
+
+
+def encoder_forward(w: W, dims: T5Dims, input_ids: torch.Tensor, attention_mask: torch.Tensor,
+                    linear=_lin) -> torch.Tensor:
+    """HF T5 encoder stack: [B,S] ids -> [B,S,d] (final layer norm applied).
+
+    ``linear`` lets tools/precision_probe.py swap the projections for emulated tensor-core arithmetic."""
     H, dk = dims.num_heads, dims.d_kv
     x = w["shared.weight"][input_ids]
     B, S, _ = x.shape
@@ -87,12 +95,12 @@ def encoder_forward(w: W, dims: T5Dims, input_ids: torch.Tensor, attention_mask:
     for i in range(dims.num_layers):
         p = f"encoder.block.{i}.layer."
         h = rmsnorm(x, w[p + "0.layer_norm.weight"], dims.eps)
-        q = _heads(h @ w[p + "0.SelfAttention.q.weight"].t(), H, dk)
-        k = _heads(h @ w[p + "0.SelfAttention.k.weight"].t(), H, dk)
-        v = _heads(h @ w[p + "0.SelfAttention.v.weight"].t(), H, dk)
-        x = x + _attend(q, k, v, bias) @ w[p + "0.SelfAttention.o.weight"].t()
+        q = _heads(linear(h, w[p + "0.SelfAttention.q.weight"]), H, dk)
+        k = _heads(linear(h, w[p + "0.SelfAttention.k.weight"]), H, dk)
+        v = _heads(linear(h, w[p + "0.SelfAttention.v.weight"]), H, dk)
+        x = x + linear(_attend(q, k, v, bias), w[p + "0.SelfAttention.o.weight"])
         h = rmsnorm(x, w[p + "1.layer_norm.weight"], dims.eps)
-        x = x + torch.relu(h @ w[p + "1.DenseReluDense.wi.weight"].t()) @ w[p + "1.DenseReluDense.wo.weight"].t()
+        x = x + linear(torch.relu(linear(h, w[p + "1.DenseReluDense.wi.weight"])), w[p + "1.DenseReluDense.wo.weight"])
     return rmsnorm(x, w["encoder.final_layer_norm.weight"], dims.eps)
 
 
@@ -156,8 +164,8 @@ class CachedDecoder:
     Cross K/V are projected once per query; self K/V are kept per row and reordered by ``reorder``.
     """
 
-    def __init__(self, w: W, dims: T5Dims, enc: torch.Tensor, enc_mask: torch.Tensor, nb: int):
-        self.w, self.dims, self.nb = w, dims, nb
+    def __init__(self, w: W, dims: T5Dims, enc: torch.Tensor, enc_mask: torch.Tensor, nb: int, linear=_lin):
+        self.w, self.dims, self.nb, self.lin = w, dims, nb, linear
         H, dk = dims.num_heads, dims.d_kv
         self.B = enc.shape[0]
         neg = torch.finfo(torch.float32).min
@@ -165,8 +173,8 @@ class CachedDecoder:
         self.ck, self.cv = [], []
         for i in range(dims.num_decoder_layers):
             p = f"decoder.block.{i}.layer.1.EncDecAttention."
-            self.ck.append(_heads(enc @ w[p + "k.weight"].t(), H, dk))                   # [B,H,S,dk]
-            self.cv.append(_heads(enc @ w[p + "v.weight"].t(), H, dk))
+            self.ck.append(_heads(linear(enc, w[p + "k.weight"]), H, dk))                   # [B,H,S,dk]
+            self.cv.append(_heads(linear(enc, w[p + "v.weight"]), H, dk))
         self.sk: List[Optional[torch.Tensor]] = [None] * dims.num_decoder_layers          # [R,H,t,dk]
         self.sv: List[Optional[torch.Tensor]] = [None] * dims.num_decoder_layers
         self.rel = w["decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"]
@@ -179,7 +187,7 @@ class CachedDecoder:
 
     def step(self, last_tokens: Optional[torch.Tensor]) -> torch.Tensor:
         """Position ``self.t`` for all R = B*nb rows; ``last_tokens`` [R] (None at t=0). Returns logits [R,V]."""
-        w, dims, t = self.w, self.dims, self.t
+        w, dims, t, linear = self.w, self.dims, self.t, self.lin
         H, dk, R = dims.num_heads, dims.d_kv, self.B * self.nb
         if t == 0:
             x = w["start_token_embed"].expand(R, 1, -1)
@@ -189,22 +197,22 @@ class CachedDecoder:
         for i in range(dims.num_decoder_layers):
             p = f"decoder.block.{i}.layer."
             h = rmsnorm(x, w[p + "0.layer_norm.weight"], dims.eps)
-            q = _heads(h @ w[p + "0.SelfAttention.q.weight"].t(), H, dk)
-            k = _heads(h @ w[p + "0.SelfAttention.k.weight"].t(), H, dk)
-            v = _heads(h @ w[p + "0.SelfAttention.v.weight"].t(), H, dk)
+            q = _heads(linear(h, w[p + "0.SelfAttention.q.weight"]), H, dk)
+            k = _heads(linear(h, w[p + "0.SelfAttention.k.weight"]), H, dk)
+            v = _heads(linear(h, w[p + "0.SelfAttention.v.weight"]), H, dk)
             self.sk[i] = k if t == 0 else torch.cat([self.sk[i], k], dim=2)
             self.sv[i] = v if t == 0 else torch.cat([self.sv[i], v], dim=2)
-            x = x + _attend(q, self.sk[i], self.sv[i], bias) @ w[p + "0.SelfAttention.o.weight"].t()
+            x = x + linear(_attend(q, self.sk[i], self.sv[i], bias), w[p + "0.SelfAttention.o.weight"])
             h = rmsnorm(x, w[p + "1.layer_norm.weight"], dims.eps)
-            q = _heads(h @ w[p + "1.EncDecAttention.q.weight"].t(), H, dk).view(self.B, self.nb, H, 1, dk)
+            q = _heads(linear(h, w[p + "1.EncDecAttention.q.weight"]), H, dk).view(self.B, self.nb, H, 1, dk)
             sc = torch.einsum("bnhqd,bhsd->bnhqs", q, self.ck[i]) + self.cross_bias[:, None]
             pr = torch.softmax(sc.float(), dim=-1)
             o = torch.einsum("bnhqs,bhsd->bnhqd", pr, self.cv[i]).reshape(R, H, 1, dk)
-            x = x + o.transpose(1, 2).reshape(R, 1, H * dk) @ w[p + "1.EncDecAttention.o.weight"].t()
+            x = x + linear(o.transpose(1, 2).reshape(R, 1, H * dk), w[p + "1.EncDecAttention.o.weight"])
             h = rmsnorm(x, w[p + "2.layer_norm.weight"], dims.eps)
-            x = x + torch.relu(h @ w[p + "2.DenseReluDense.wi.weight"].t()) @ w[p + "2.DenseReluDense.wo.weight"].t()
+            x = x + linear(torch.relu(linear(h, w[p + "2.DenseReluDense.wi.weight"])), w[p + "2.DenseReluDense.wo.weight"])
         x = rmsnorm(x, w["decoder.final_layer_norm.weight"], dims.eps)
         if dims.scaleup_output_hidden:
             x = x * (dims.d_model ** -0.5)
         self.t += 1
-        return x[:, 0, :] @ output_table(w, dims, t).t()
+        return linear(x[:, 0, :], output_table(w, dims, t))

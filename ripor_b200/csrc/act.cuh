@@ -1,0 +1,105 @@
+// Activation operand buffers ("ActBuf"): what every GEMM of the engine reads as its A operand.
+//
+// The tensor-core GEMMs run on error-compensated splits of the fp32 activations, so producers (RMSNorm,
+// attention, the ReLU epilogue) write the operand already split into planes:
+//   RB200_PREC_FP32    plane 0 = raw fp32
+//   RB200_PREC_TF32X3  plane 0 = tf32(x), plane 1 = tf32(x - plane0), both stored as fp32 words
+//   RB200_PREC_BF16X3  plane 0 = bf16(x), plane 1 = bf16(x - plane0)
+//   RB200_PREC_TF32    plane 0 = tf32(x)
+//   RB200_PREC_BF16    plane 0 = bf16(x)
+// `plane` is the element distance between the planes (row capacity * row length).
+#pragma once
+#include <cuda_bf16.h>
+#include <cstdint>
+
+namespace rb {
+
+struct ActOut {
+  void* base;
+  int64_t plane;   // elements between plane 0 and plane 1
+  int mode;        // rb200_precision
+};
+
+__host__ __device__ inline int prec_planes(int mode) { return (mode == 1 || mode == 2) ? 2 : 1; }
+__host__ __device__ inline int prec_elem_bytes(int mode) { return (mode == 2 || mode == 4) ? 2 : 4; }
+
+// round-to-nearest-even to the 10-bit tf32 mantissa, kept as an fp32 word with the low 13 bits cleared
+__host__ __device__ inline float round_tf32(float x) {
+#ifdef __CUDA_ARCH__
+  uint32_t b = __float_as_uint(x);
+#else
+  uint32_t b;
+  memcpy(&b, &x, 4);
+#endif
+  if ((b & 0x7f800000u) != 0x7f800000u) b = (b + 0xfffu + ((b >> 13) & 1u)) & 0xffffe000u;
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(b);
+#else
+  float r;
+  memcpy(&r, &b, 4);
+  return r;
+#endif
+}
+
+__device__ __forceinline__ void act_store(const ActOut& o, int64_t idx, float v) {
+  switch (o.mode) {
+    case 0:
+      static_cast<float*>(o.base)[idx] = v;
+      break;
+    case 1: {
+      const float hi = round_tf32(v);
+      static_cast<float*>(o.base)[idx] = hi;
+      static_cast<float*>(o.base)[o.plane + idx] = round_tf32(v - hi);
+      break;
+    }
+    case 2: {
+      const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+      static_cast<__nv_bfloat16*>(o.base)[idx] = hi;
+      static_cast<__nv_bfloat16*>(o.base)[o.plane + idx] = __float2bfloat16_rn(v - __bfloat162float(hi));
+      break;
+    }
+    case 3:
+      static_cast<float*>(o.base)[idx] = round_tf32(v);
+      break;
+    default:
+      static_cast<__nv_bfloat16*>(o.base)[idx] = __float2bfloat16_rn(v);
+      break;
+  }
+}
+
+// four consecutive elements, idx % 4 == 0 (vector stores)
+__device__ __forceinline__ void act_store4(const ActOut& o, int64_t idx, float4 v) {
+  switch (o.mode) {
+    case 0:
+      *reinterpret_cast<float4*>(static_cast<float*>(o.base) + idx) = v;
+      break;
+    case 1: {
+      float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      float4 lo = make_float4(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y), round_tf32(v.z - hi.z),
+                              round_tf32(v.w - hi.w));
+      *reinterpret_cast<float4*>(static_cast<float*>(o.base) + idx) = hi;
+      *reinterpret_cast<float4*>(static_cast<float*>(o.base) + o.plane + idx) = lo;
+      break;
+    }
+    case 3: {
+      float4 hi = make_float4(round_tf32(v.x), round_tf32(v.y), round_tf32(v.z), round_tf32(v.w));
+      *reinterpret_cast<float4*>(static_cast<float*>(o.base) + idx) = hi;
+      break;
+    }
+    default: {   // bf16 planes
+      __nv_bfloat16* b = static_cast<__nv_bfloat16*>(o.base);
+      const float f[4] = {v.x, v.y, v.z, v.w};
+      __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        hi[i] = __float2bfloat16_rn(f[i]);
+        lo[i] = __float2bfloat16_rn(f[i] - __bfloat162float(hi[i]));
+      }
+      *reinterpret_cast<uint2*>(b + idx) = *reinterpret_cast<uint2*>(hi);
+      if (o.mode == 2) *reinterpret_cast<uint2*>(b + o.plane + idx) = *reinterpret_cast<uint2*>(lo);
+      break;
+    }
+  }
+}
+
+}  // namespace rb

@@ -1,0 +1,339 @@
+// Prefix-constrained beam step and finalize on the GPU (integer trie walk + float64 candidate ranking).
+//
+// One CTA per query. Per step it restates, bit for bit on the float64 side, what the reference does in
+// t5_pretrainer/tasks/generation.py:
+//   :453-458  s = log_softmax(logits) if apply_log_softmax_for_scores else logits          (fp32)
+//   :461      valid_mask from the DocID trie (here: walked in HBM, no host round trip)
+//   :462      processed = s + (1 - valid_mask) * (-1e9)                                     (float64)
+//   :463      cand = processed + beam_scores[:, None]                                       (float64)
+//   :485-492  top-2*nb over the nb*V candidates of a query, parent = idx // V, token = idx % V
+//   :496-507  BeamSearchScorer.process with eos=None keeps the first nb of them
+//   :511      input_ids = cat(input_ids[beam_idx], tokens)
+// plus the bookkeeping the KV-cached decoder needs instead of _reorder_cache (:517-518): a per-beam
+// ancestry table saying which row holds the K/V of each earlier position.
+// Ties between exactly equal candidates (only possible between -1e9-penalised duplicates) go to the lower
+// flat index; torch.topk leaves that order unspecified.
+#include <cfloat>
+#include <climits>
+#include <cmath>
+
+#include "beam.h"
+
+using rb::TrieState;
+using rb::TrieView;
+
+namespace {
+
+constexpr int kMaxPerThread = 128;   // candidates owned by one thread, tracked in a 128-bit taken mask
+
+__device__ __forceinline__ bool cand_better(double va, int ia, double vb, int ib) {
+  return va > vb || (va == vb && ia < ib);
+}
+
+struct StepArgs {
+  TrieView tv;
+  int t, nb, rpq, apply_ls, L, d_model;
+  const float* logits;
+  const double* sc_old;
+  const TrieState* st_old;
+  const int32_t* hist_old;
+  const int32_t* anc_old;
+  double* sc_new;
+  TrieState* st_new;
+  int32_t* hist_new;
+  int32_t* anc_new;
+  int32_t* parent_out;
+  int32_t* token_out;
+  const float* embed_table;
+  float* next_x;
+};
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
+  constexpr int NW = THREADS / 32;
+  const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nb = a.nb, V = a.tv.V, words = a.tv.words, t = a.t;
+  const int total = nb * V;
+
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* bs = reinterpret_cast<double*>(smem_raw);            // [nb]
+  double* win_val = bs + nb;                                    // [nb]
+  double* red_val = win_val + nb;                               // [32]
+  int* red_idx = reinterpret_cast<int*>(red_val + 32);          // [32]
+  int* win_idx = red_idx + 32;                                  // [nb]
+  float* row_max = reinterpret_cast<float*>(win_idx + nb);      // [nb]
+  float* row_log = row_max + nb;                                // [nb]
+  uint32_t* allow = reinterpret_cast<uint32_t*>(row_log + nb);  // [nb, words]
+
+  // ---- A. allowed-children bitmap of every beam (trie walk state -> V bits) -------------------------
+  for (int i = warp; i < nb; i += NW) {
+    const TrieState s = a.st_old[b * nb + i];
+    uint32_t* bm = allow + i * words;
+    const int n = s.hi - s.lo;
+    for (int w = lane; w < words; w += 32)
+      bm[w] = (n > 0 && s.node >= 0 && t < a.tv.L) ? a.tv.node_bitmap[(int64_t)s.node * words + w] : 0u;
+    __syncwarp();
+    if (n > 0 && s.node < 0 && t < a.tv.L && lane < n) {
+      const int v = rb::trie_code(a.tv, (int64_t)s.lo + lane, t);
+      atomicOr(&bm[v >> 5], 1u << (v & 31));
+    }
+    if (lane == 0) bs[i] = a.sc_old[b * nb + i];
+    // ---- A2. optional fp32 log-softmax statistics of the beam's logits row -------------------------
+    if (a.apply_ls) {
+      const float* row = a.logits + (int64_t)(b * a.rpq + (a.rpq == 1 ? 0 : i)) * V;
+      float m = -INFINITY;
+      for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int v = lane; v < V; v += 32) sum += expf(row[v] - m);
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) { row_max[i] = m; row_log[i] = logf(sum); }
+    }
+  }
+  __syncthreads();
+
+  // ---- B. float64 candidate values; iterative arg-max for the best nb ------------------------------
+  auto cand_val = [&](int c) -> double {
+    const int i = c / V, v = c - i * V;
+    float x = a.logits[(int64_t)(b * a.rpq + (a.rpq == 1 ? 0 : i)) * V + v];
+    if (a.apply_ls) x = (x - row_max[i]) - row_log[i];
+    const bool ok = (allow[i * words + (v >> 5)] >> (v & 31)) & 1u;
+    const double processed = ok ? (double)x : (double)x + (-1e9);   // s + (1 - mask) * (-1e9)
+    return processed + bs[i];
+  };
+  uint32_t taken[kMaxPerThread / 32] = {0u, 0u, 0u, 0u};
+  const int K = (total + THREADS - 1) / THREADS;
+  double best_v;
+  int best_c;
+  auto rescan = [&]() {
+    best_v = -INFINITY;
+    best_c = INT_MAX;
+    for (int k = 0; k < K; ++k) {
+      const int c = tid + k * THREADS;
+      if (c < total && !((taken[k >> 5] >> (k & 31)) & 1u)) {
+        const double v = cand_val(c);
+        if (cand_better(v, c, best_v, best_c)) { best_v = v; best_c = c; }
+      }
+    }
+  };
+  rescan();
+  for (int j = 0; j < nb; ++j) {
+    double v = best_v;
+    int c = best_c;
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_down_sync(0xffffffffu, v, o);
+      const int oc = __shfl_down_sync(0xffffffffu, c, o);
+      if (cand_better(ov, oc, v, c)) { v = ov; c = oc; }
+    }
+    if (lane == 0) { red_val[warp] = v; red_idx[warp] = c; }
+    __syncthreads();
+    if (warp == 0) {
+      v = lane < NW ? red_val[lane] : -INFINITY;
+      c = lane < NW ? red_idx[lane] : INT_MAX;
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_down_sync(0xffffffffu, v, o);
+        const int oc = __shfl_down_sync(0xffffffffu, c, o);
+        if (cand_better(ov, oc, v, c)) { v = ov; c = oc; }
+      }
+      if (lane == 0) { win_val[j] = v; win_idx[j] = c; }
+    }
+    __syncthreads();
+    c = win_idx[j];
+    if (c != INT_MAX && (c % THREADS) == tid) {
+      const int k = c / THREADS;
+      taken[k >> 5] |= 1u << (k & 31);
+      rescan();
+    }
+  }
+
+  // ---- C. new beam state: scores, trie child, token history, KV ancestry, next decoder input --------
+  for (int j = tid; j < nb; j += THREADS) {
+    const int c = win_idx[j];
+    const int i = c / V, v = c - i * V;
+    const int r_new = b * nb + j;
+    a.sc_new[r_new] = win_val[j];
+    a.parent_out[r_new] = i;
+    a.token_out[r_new] = v;
+    a.st_new[r_new] = rb::trie_child(a.tv, a.st_old[b * nb + i], t, v);
+  }
+  const int L = a.L;
+  for (int e = tid; e < nb * L; e += THREADS) {
+    const int j = e / L, p = e - j * L;
+    const int c = win_idx[j];
+    const int i = c / V, v = c - i * V;
+    const int src = b * nb + i, dst = b * nb + j;
+    a.hist_new[dst * L + p] = p < t ? a.hist_old[src * L + p] : (p == t ? v : 0);
+    int anc;
+    if (p < t) anc = a.anc_old[src * L + p];
+    else if (p == t) anc = (a.rpq == 1) ? b : src;    // the row that ran position t for this lineage
+    else if (p == t + 1) anc = dst;                   // next step attends to itself at position t+1
+    else anc = 0;
+    a.anc_new[dst * L + p] = anc;
+  }
+  if (a.embed_table != nullptr) {
+    const int d = a.d_model;
+    for (int e = tid; e < nb * d; e += THREADS) {
+      const int j = e / d, col = e - j * d;
+      const int v = win_idx[j] % V;
+      a.next_x[(int64_t)(b * nb + j) * d + col] = a.embed_table[(int64_t)v * d + col];
+    }
+  }
+}
+
+__global__ void beam_reset_kernel(TrieView tv, int nb, int L, int batch, double* sc, TrieState* st, int32_t* hist,
+                                  int32_t* anc) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= batch * nb) return;
+  const int b = r / nb, i = r - b * nb;
+  sc[r] = (i == 0) ? 0.0 : (double)(-1e9f);   // fp32 zeros with [:, 1:] = -1e9 (generation.py:418-420)
+  st[r] = rb::trie_root(tv);
+  for (int p = 0; p < L; ++p) { hist[r * L + p] = 0; anc[r * L + p] = (p == 0) ? b : 0; }
+}
+
+__global__ void beam_finalize_kernel(int nb, int L, int steps, int keep, double length_penalty,
+                                     const double* __restrict__ sc, const TrieState* __restrict__ st,
+                                     const int32_t* __restrict__ hist, int64_t* __restrict__ seqs,
+                                     float* __restrict__ scores, int32_t* __restrict__ leaf) {
+  // HF 4.17 BeamSearchScorer.finalize with eos=None: every beam becomes a hypothesis with
+  // score / len**length_penalty (float64); sorted ascending (stable) and popped from the end.
+  extern __shared__ double hs[];
+  const int b = blockIdx.x;
+  const double denom = pow((double)(steps + 1), length_penalty);
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) hs[j] = sc[b * nb + j] / denom;
+  __syncthreads();
+  for (int j = threadIdx.x; j < nb; j += blockDim.x) {
+    int rank = 0;
+    for (int k = 0; k < nb; ++k) rank += (hs[k] > hs[j]) || (hs[k] == hs[j] && k > j);
+    if (rank >= keep) continue;
+    const int64_t o = (int64_t)b * keep + rank;
+    const int r = b * nb + j;
+    seqs[o * (steps + 1)] = 0;   // decoder_start_token_id
+    for (int p = 0; p < steps; ++p) seqs[o * (steps + 1) + 1 + p] = hist[r * L + p];
+    scores[o] = (float)hs[j];
+    if (leaf) { leaf[o * 2] = st[r].lo; leaf[o * 2 + 1] = st[r].hi; }
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rb200_beam_create(int device, int max_batch, int num_beams, int L, int V, rb200_beam** out) {
+  RB_REQUIRE(out, "null argument");
+  RB_REQUIRE(max_batch >= 1 && num_beams >= 1 && L >= 1 && V >= 1, "need max_batch, num_beams, L, V >= 1");
+  RB_REQUIRE((int64_t)num_beams * V <= 1024 * kMaxPerThread, "num_beams*V=%lld exceeds the beam kernel limit %d",
+             (long long)num_beams * V, 1024 * kMaxPerThread);
+  rb200_beam* bm = new (std::nothrow) rb200_beam();
+  if (!bm) return rb::fail(RB200_ERR_NOMEM, "out of memory");
+  bm->device = device; bm->max_batch = max_batch; bm->nb = num_beams; bm->L = L; bm->V = V;
+  int prev = 0;
+  RB_CUDA(cudaGetDevice(&prev));
+  RB_CUDA(cudaSetDevice(device));
+  const size_t R = (size_t)max_batch * num_beams;
+  for (int h = 0; h < 2; ++h) {
+    RB_CUDA(cudaMalloc(&bm->scores[h], R * sizeof(double)));
+    RB_CUDA(cudaMalloc(&bm->state[h], R * sizeof(TrieState)));
+    RB_CUDA(cudaMalloc(&bm->hist[h], R * L * sizeof(int32_t)));
+    RB_CUDA(cudaMalloc(&bm->anc[h], R * L * sizeof(int32_t)));
+  }
+  RB_CUDA(cudaMalloc(&bm->parent, R * sizeof(int32_t)));
+  RB_CUDA(cudaMalloc(&bm->token, R * sizeof(int32_t)));
+  RB_CUDA(cudaSetDevice(prev));
+  *out = bm;
+  return 0;
+}
+
+int rb200_beam_free(rb200_beam* bm) {
+  if (!bm) return 0;
+  for (int h = 0; h < 2; ++h) {
+    cudaFree(bm->scores[h]); cudaFree(bm->state[h]); cudaFree(bm->hist[h]); cudaFree(bm->anc[h]);
+  }
+  cudaFree(bm->parent); cudaFree(bm->token);
+  delete bm;
+  return 0;
+}
+
+int rb200_beam_reset(rb200_beam* bm, const rb200_trie* trie, int batch, void* stream) {
+  RB_REQUIRE(bm && trie, "null argument");
+  RB_REQUIRE(batch >= 1 && batch <= bm->max_batch, "batch %d outside [1, %d]", batch, bm->max_batch);
+  RB_REQUIRE(trie->V == bm->V, "trie V=%d but beam state was created for V=%d", trie->V, bm->V);
+  if (trie->device != bm->device)
+    return rb::fail(RB200_ERR_STATE, "trie is on device %d, beam state on device %d: call rb200_trie_upload",
+                    trie->device, bm->device);
+  bm->batch = batch; bm->step = 0; bm->cur = 0;
+  const int R = batch * bm->nb;
+  beam_reset_kernel<<<rb::ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(
+      trie->device_view(), bm->nb, bm->L, batch, bm->scores[0], bm->state[0], bm->hist[0], bm->anc[0]);
+  RB_CUDA(cudaGetLastError());
+  rb::launch_count()++;
+  return 0;
+}
+
+int rb200_beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits, int rows_per_query,
+                    int apply_log_softmax, const float* embed_table, float* next_x, int d_model, void* stream) {
+  RB_REQUIRE(bm && trie && logits, "null argument");
+  RB_REQUIRE(bm->batch >= 1, "rb200_beam_reset has not been called");
+  RB_REQUIRE(rows_per_query == 1 || rows_per_query == bm->nb, "rows_per_query must be 1 or num_beams=%d", bm->nb);
+  RB_REQUIRE(bm->step < bm->L, "already took L=%d steps", bm->L);
+  RB_REQUIRE(bm->step < trie->L, "step %d exceeds the trie depth %d", bm->step, trie->L);
+  RB_REQUIRE((embed_table == nullptr) == (next_x == nullptr), "embed table and next_x must be given together");
+  StepArgs a;
+  a.tv = trie->device_view();
+  a.t = bm->step; a.nb = bm->nb; a.rpq = rows_per_query; a.apply_ls = apply_log_softmax; a.L = bm->L;
+  a.d_model = d_model;
+  a.logits = logits;
+  const int o = bm->cur, n = bm->cur ^ 1;
+  a.sc_old = bm->scores[o]; a.st_old = bm->state[o]; a.hist_old = bm->hist[o]; a.anc_old = bm->anc[o];
+  a.sc_new = bm->scores[n]; a.st_new = bm->state[n]; a.hist_new = bm->hist[n]; a.anc_new = bm->anc[n];
+  a.parent_out = bm->parent; a.token_out = bm->token;
+  a.embed_table = embed_table; a.next_x = next_x;
+  const int nb = bm->nb;
+  const size_t smem = (2 * nb + 32) * sizeof(double) + (32 + nb) * sizeof(int) + 2 * nb * sizeof(float) +
+                      (size_t)nb * a.tv.words * sizeof(uint32_t);
+  const int64_t total = (int64_t)nb * bm->V;
+  if (total <= 256 * 32) {
+    beam_step_kernel<256><<<bm->batch, 256, smem, (cudaStream_t)stream>>>(a);
+  } else {
+    beam_step_kernel<1024><<<bm->batch, 1024, smem, (cudaStream_t)stream>>>(a);
+  }
+  RB_CUDA(cudaGetLastError());
+  rb::launch_count()++;
+  bm->cur = n;
+  bm->step += 1;
+  return 0;
+}
+
+int rb200_beam_finalize(rb200_beam* bm, const rb200_trie* trie, int num_return, double length_penalty,
+                        int64_t* sequences, float* scores, int32_t* leaf, void* stream) {
+  RB_REQUIRE(bm && sequences && scores, "null argument");
+  RB_REQUIRE(bm->batch >= 1 && bm->step >= 1, "no step has been taken");
+  RB_REQUIRE(num_return >= 1 && num_return <= bm->nb,
+             "`num_return_sequences` has to be smaller or equal to `num_beams`.");
+  (void)trie;
+  const int c = bm->cur;
+  beam_finalize_kernel<<<bm->batch, 128, bm->nb * sizeof(double), (cudaStream_t)stream>>>(
+      bm->nb, bm->L, bm->step, num_return, length_penalty, bm->scores[c], bm->state[c], bm->hist[c], sequences,
+      scores, leaf);
+  RB_CUDA(cudaGetLastError());
+  rb::launch_count()++;
+  return 0;
+}
+
+int rb200_beam_view(const rb200_beam* bm, int what, const void** ptr) {
+  RB_REQUIRE(bm && ptr, "null argument");
+  const int c = bm->cur;
+  switch (what) {
+    case 0: *ptr = bm->scores[c]; break;
+    case 1: *ptr = bm->parent; break;
+    case 2: *ptr = bm->token; break;
+    case 3: *ptr = bm->hist[c]; break;
+    case 4: *ptr = bm->anc[c]; break;
+    case 5: *ptr = bm->state[c]; break;
+    default: return rb::fail(RB200_ERR_INVALID, "unknown view %d", what);
+  }
+  return 0;
+}
+
+int rb200_beam_current_step(const rb200_beam* bm) { return bm ? bm->step : RB200_ERR_INVALID; }
+
+}  // extern "C"

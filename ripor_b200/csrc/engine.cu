@@ -1,0 +1,615 @@
+// Engine: T5 encoder + KV-cached decoder + constrained beam search for one GPU, behind the C ABI.
+//
+// Replaces generate_for_constrained_prefix_beam_search (reference t5_pretrainer/tasks/generation.py:35-251)
+// and the model forward it drives every step (t5_pretrainer/modeling/t5_generative_retriever.py:295-450).
+// Differences in HOW (not in results): the encoder states are never expanded x num_beams
+// (generation.py:231-233) - cross K/V are projected once per query and shared by its beams; the decoder
+// runs one position per step against a KV cache addressed through the beam ancestry table instead of
+// re-running the whole prefix (finding 4) and instead of _reorder_cache copies
+// (t5_generative_retriever.py:484-512); step 0 runs one row per query because all beams are identical.
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "beam.h"
+#include "kernels.h"
+
+using rb::ActOut;
+using rb::GemmArgs;
+
+namespace {
+
+struct Packed {          // a weight matrix [N, K] in the planes of the engine precision
+  void* ptr = nullptr;
+  int64_t plane = 0;     // elements between planes
+  int64_t N = 0, K = 0;
+};
+
+struct Layer {
+  Packed qkv, o, wi, wo;           // self-attention fused q|k|v, output, feed-forward
+  Packed cq, co;                   // decoder cross-attention query / output
+  float* ln0 = nullptr;
+  float* ln1 = nullptr;
+  float* ln2 = nullptr;
+};
+
+}  // namespace
+
+struct rb200_engine {
+  rb200_engine_config cfg;
+  int mode = 0, planes = 1, elem = 4;
+  int d = 0, inner = 0, dff = 0, H = 0, V = 0, Lmodel = 0;
+  std::vector<Layer> enc, dec;
+  Packed ckv;                      // all decoder layers' cross K|V projections: [Nl*2*inner, d]
+  std::vector<Packed> out_tab;     // per position output table [V, d]
+  std::vector<float*> in_tab;      // per position input table fp32 [V, d]
+  float* shared_emb = nullptr;     // [vocab, d]
+  float* start_emb = nullptr;      // [d]
+  float* enc_final_ln = nullptr;
+  float* dec_final_ln = nullptr;
+  std::vector<float> enc_rel_host, dec_rel_host;   // [num_buckets, H]
+  float* dec_bias = nullptr;       // [H, Lmodel]
+  float* enc_bias = nullptr;       // [H, 2*S-1]
+  int enc_bias_S = 0;
+  std::set<std::string> have;
+  bool finalized = false;
+  // workspaces
+  int64_t Mcap = 0, Rcap = 0, BScap = 0;
+  float* x = nullptr;              // [Mcap, d] residual stream
+  void* xn = nullptr;              // ActBuf [planes][Mcap][d]
+  float* qkv = nullptr;            // [Mcap, 3*inner]
+  float* q2 = nullptr;             // [Mcap, inner]
+  void* ctx = nullptr;             // ActBuf [planes][Mcap][inner]
+  void* hbuf = nullptr;            // ActBuf [planes][Mcap][dff]
+  float* logits = nullptr;         // [Rcap, V]
+  float* cross_kv = nullptr;       // [BScap, Nl*2*inner]
+  float* enc_out = nullptr;        // [BScap, d]
+  float* cache_k = nullptr;        // [Nl][Lmodel][Rcap][inner]
+  float* cache_v = nullptr;
+  int64_t* ids_dev = nullptr;      // host-call staging
+  int64_t* mask_dev = nullptr;
+  int64_t* seq_dev = nullptr;
+  float* score_dev = nullptr;
+  int32_t* leaf_dev = nullptr;
+  int64_t ws_bytes = 0;
+  rb200_beam* beam = nullptr;
+  // batch in flight
+  int B = 0, S = 0, nb = 0;
+  const int64_t* cur_mask = nullptr;
+  int64_t launches = 0;
+  // optional per-GEMM event timing (rb200_engine_set_profiling)
+  bool profiling = false;
+  std::vector<cudaEvent_t> events;
+  size_t ev_used = 0;
+  double prof_flops = 0.0;
+
+  ActOut act(void* base, int64_t row_len) const { return ActOut{base, Mcap * row_len, mode}; }
+};
+
+namespace {
+
+int dev_alloc(rb200_engine* e, void** p, int64_t bytes) {
+  RB_CUDA(cudaMalloc(p, (size_t)(bytes > 0 ? bytes : 16)));
+  e->ws_bytes += bytes;
+  return 0;
+}
+
+int alloc_packed(rb200_engine* e, Packed* w, int64_t N, int64_t K) {
+  w->N = N; w->K = K; w->plane = N * K;
+  return dev_alloc(e, &w->ptr, (int64_t)e->planes * N * K * e->elem);
+}
+
+// pack `rows` x K fp32 rows into row offset `row0` of packed weight w
+int pack_rows(rb200_engine* e, Packed* w, int64_t row0, const float* src, int64_t rows, cudaStream_t s) {
+  char* dst = static_cast<char*>(w->ptr) + row0 * w->K * e->elem;
+  return rb::launch_pack_planes(src, dst, rows * w->K, w->plane, e->mode, s);
+}
+
+int copy_f32(float* dst, const float* src, int64_t n, cudaStream_t s) {
+  RB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * 4, cudaMemcpyDeviceToDevice, s));
+  return 0;
+}
+
+int gemm(rb200_engine* e, const void* A, int64_t a_row_len, const Packed& w, float* C, int64_t ldc, ActOut act,
+         int64_t M, int epi, cudaStream_t s) {
+  GemmArgs g;
+  g.mode = e->mode;
+  g.A = A; g.a_plane = e->Mcap * a_row_len;
+  g.W = w.ptr; g.w_plane = w.plane;
+  g.C = C; g.ldc = ldc; g.act = act;
+  g.M = M; g.N = w.N; g.K = w.K; g.epilogue = epi;
+  if (!e->profiling) return rb::launch_gemm(g, s);
+  // profiling pass: bracket every GEMM launch with events on its own stream (bench.py roofline leg)
+  if (e->ev_used + 2 > e->events.size()) {
+    const size_t old = e->events.size();
+    e->events.resize(old + 1024);
+    for (size_t i = old; i < e->events.size(); ++i) RB_CUDA(cudaEventCreate(&e->events[i]));
+  }
+  RB_CUDA(cudaEventRecord(e->events[e->ev_used], s));
+  const int st = rb::launch_gemm(g, s);
+  RB_CUDA(cudaEventRecord(e->events[e->ev_used + 1], s));
+  e->ev_used += 2;
+  e->prof_flops += 2.0 * (double)M * (double)w.N * (double)w.K;
+  return st;
+}
+
+int build_bias_tables(rb200_engine* e, int S, cudaStream_t s) {
+  const auto& c = e->cfg;
+  if (e->dec_bias == nullptr) {
+    std::vector<float> t((size_t)e->H * e->Lmodel);
+    for (int h = 0; h < e->H; ++h)
+      for (int dist = 0; dist < e->Lmodel; ++dist)
+        t[(size_t)h * e->Lmodel + dist] =
+            e->dec_rel_host[(size_t)rb::relative_bucket(-dist, false, c.num_buckets, c.max_distance) * e->H + h];
+    RB_TRY(dev_alloc(e, (void**)&e->dec_bias, (int64_t)t.size() * 4));
+    RB_CUDA(cudaMemcpyAsync(e->dec_bias, t.data(), t.size() * 4, cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaStreamSynchronize(s));
+  }
+  if (S > 0 && S != e->enc_bias_S) {
+    std::vector<float> t((size_t)e->H * (2 * S - 1));
+    for (int h = 0; h < e->H; ++h)
+      for (int off = 0; off < 2 * S - 1; ++off)
+        t[(size_t)h * (2 * S - 1) + off] =
+            e->enc_rel_host[(size_t)rb::relative_bucket(off - (S - 1), true, c.num_buckets, c.max_distance) * e->H + h];
+    if (e->enc_bias == nullptr)
+      RB_TRY(dev_alloc(e, (void**)&e->enc_bias, (int64_t)e->H * (2 * c.max_src_len - 1) * 4));
+    RB_CUDA(cudaMemcpyAsync(e->enc_bias, t.data(), t.size() * 4, cudaMemcpyHostToDevice, s));
+    RB_CUDA(cudaStreamSynchronize(s));
+    e->enc_bias_S = S;
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
+  RB_REQUIRE(cfg && out, "null argument");
+  RB_REQUIRE(cfg->d_kv == 64, "d_kv must be 64 (t5-base/large), got %d", cfg->d_kv);
+  RB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 4, "unknown precision %d", cfg->precision);
+  RB_REQUIRE(cfg->d_model % 8 == 0 && cfg->d_ff % 8 == 0, "d_model and d_ff must be multiples of 8");
+  RB_REQUIRE(cfg->decoder_vocab_size % 4 == 0, "decoder_vocab_size must be a multiple of 4");
+  RB_REQUIRE(cfg->max_batch >= 1 && cfg->max_beams >= 1 && cfg->max_src_len >= 1 && cfg->docid_len >= 1,
+             "max_batch, max_beams, max_src_len, docid_len must be >= 1");
+  int ndev = 0;
+  RB_CUDA(cudaGetDeviceCount(&ndev));
+  RB_REQUIRE(cfg->device >= 0 && cfg->device < ndev, "device %d not present (%d devices)", cfg->device, ndev);
+  RB_CUDA(cudaSetDevice(cfg->device));
+  rb200_engine* e = new (std::nothrow) rb200_engine();
+  if (!e) return rb::fail(RB200_ERR_NOMEM, "out of memory");
+  e->cfg = *cfg;
+  e->mode = cfg->precision;
+  e->planes = rb::prec_planes(e->mode);
+  e->elem = rb::prec_elem_bytes(e->mode);
+  e->d = cfg->d_model; e->H = cfg->num_heads; e->inner = cfg->num_heads * cfg->d_kv; e->dff = cfg->d_ff;
+  e->V = cfg->decoder_vocab_size; e->Lmodel = cfg->docid_len;
+  e->Rcap = (int64_t)cfg->max_batch * cfg->max_beams;
+  e->BScap = (int64_t)cfg->max_batch * cfg->max_src_len;
+  e->Mcap = std::max(e->Rcap, e->BScap);
+  const int d = e->d, inner = e->inner, dff = e->dff;
+  e->enc.resize(cfg->num_layers);
+  e->dec.resize(cfg->num_decoder_layers);
+  for (auto& l : e->enc) {
+    RB_TRY(alloc_packed(e, &l.qkv, 3 * inner, d));
+    RB_TRY(alloc_packed(e, &l.o, d, inner));
+    RB_TRY(alloc_packed(e, &l.wi, dff, d));
+    RB_TRY(alloc_packed(e, &l.wo, d, dff));
+    RB_TRY(dev_alloc(e, (void**)&l.ln0, d * 4));
+    RB_TRY(dev_alloc(e, (void**)&l.ln1, d * 4));
+  }
+  for (auto& l : e->dec) {
+    RB_TRY(alloc_packed(e, &l.qkv, 3 * inner, d));
+    RB_TRY(alloc_packed(e, &l.o, d, inner));
+    RB_TRY(alloc_packed(e, &l.cq, inner, d));
+    RB_TRY(alloc_packed(e, &l.co, d, inner));
+    RB_TRY(alloc_packed(e, &l.wi, dff, d));
+    RB_TRY(alloc_packed(e, &l.wo, d, dff));
+    RB_TRY(dev_alloc(e, (void**)&l.ln0, d * 4));
+    RB_TRY(dev_alloc(e, (void**)&l.ln1, d * 4));
+    RB_TRY(dev_alloc(e, (void**)&l.ln2, d * 4));
+  }
+  RB_TRY(alloc_packed(e, &e->ckv, (int64_t)cfg->num_decoder_layers * 2 * inner, d));
+  e->out_tab.resize(e->Lmodel);
+  e->in_tab.resize(e->Lmodel, nullptr);
+  for (int t = 0; t < e->Lmodel; ++t) {
+    RB_TRY(alloc_packed(e, &e->out_tab[t], e->V, d));
+    RB_TRY(dev_alloc(e, (void**)&e->in_tab[t], (int64_t)e->V * d * 4));
+  }
+  RB_TRY(dev_alloc(e, (void**)&e->shared_emb, (int64_t)cfg->vocab_size * d * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->start_emb, d * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->enc_final_ln, d * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->dec_final_ln, d * 4));
+  // workspaces
+  const int64_t pe = (int64_t)e->planes * e->elem;
+  RB_TRY(dev_alloc(e, (void**)&e->x, e->Mcap * d * 4));
+  RB_TRY(dev_alloc(e, &e->xn, e->Mcap * d * pe));
+  RB_TRY(dev_alloc(e, (void**)&e->qkv, e->Mcap * 3 * inner * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->q2, e->Mcap * inner * 4));
+  RB_TRY(dev_alloc(e, &e->ctx, e->Mcap * inner * pe));
+  RB_TRY(dev_alloc(e, &e->hbuf, e->Mcap * dff * pe));
+  RB_TRY(dev_alloc(e, (void**)&e->logits, e->Rcap * e->V * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->cross_kv, e->BScap * cfg->num_decoder_layers * 2 * inner * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->enc_out, e->BScap * d * 4));
+  const int64_t cache = (int64_t)cfg->num_decoder_layers * e->Lmodel * e->Rcap * inner * 4;
+  RB_TRY(dev_alloc(e, (void**)&e->cache_k, cache));
+  RB_TRY(dev_alloc(e, (void**)&e->cache_v, cache));
+  RB_TRY(dev_alloc(e, (void**)&e->ids_dev, e->BScap * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->mask_dev, e->BScap * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->seq_dev, e->Rcap * (e->Lmodel + 1) * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->score_dev, e->Rcap * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->leaf_dev, e->Rcap * 2 * 4));
+  // planes of the activation buffers may be read past M by TMA boxes: start from defined contents
+  RB_CUDA(cudaMemset(e->xn, 0, (size_t)(e->Mcap * d * pe)));
+  RB_CUDA(cudaMemset(e->ctx, 0, (size_t)(e->Mcap * inner * pe)));
+  RB_CUDA(cudaMemset(e->hbuf, 0, (size_t)(e->Mcap * dff * pe)));
+  RB_TRY(rb200_beam_create(cfg->device, cfg->max_batch, cfg->max_beams, e->Lmodel, e->V, &e->beam));
+  *out = e;
+  return 0;
+}
+
+int rb200_engine_free(rb200_engine* e) {
+  if (!e) return 0;
+  auto fp = [](Packed& p) { cudaFree(p.ptr); };
+  for (auto& l : e->enc) { fp(l.qkv); fp(l.o); fp(l.wi); fp(l.wo); cudaFree(l.ln0); cudaFree(l.ln1); }
+  for (auto& l : e->dec) {
+    fp(l.qkv); fp(l.o); fp(l.cq); fp(l.co); fp(l.wi); fp(l.wo);
+    cudaFree(l.ln0); cudaFree(l.ln1); cudaFree(l.ln2);
+  }
+  fp(e->ckv);
+  for (auto& p : e->out_tab) fp(p);
+  for (auto p : e->in_tab) cudaFree(p);
+  void* bufs[] = {e->shared_emb, e->start_emb, e->enc_final_ln, e->dec_final_ln, e->dec_bias, e->enc_bias, e->x,
+                  e->xn, e->qkv, e->q2, e->ctx, e->hbuf, e->logits, e->cross_kv, e->enc_out, e->cache_k, e->cache_v,
+                  e->ids_dev, e->mask_dev, e->seq_dev, e->score_dev, e->leaf_dev};
+  for (void* b : bufs) cudaFree(b);
+  rb200_beam_free(e->beam);
+  for (auto ev : e->events) cudaEventDestroy(ev);
+  delete e;
+  return 0;
+}
+
+int64_t rb200_engine_workspace_bytes(const rb200_engine* e) { return e ? e->ws_bytes : 0; }
+
+int rb200_engine_set_weight(rb200_engine* e, const char* name_c, const float* data, int64_t numel, void* stream) {
+  RB_REQUIRE(e && name_c && data, "null argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const std::string name(name_c);
+  const int64_t d = e->d, inner = e->inner, dff = e->dff, V = e->V;
+  auto expect = [&](int64_t n) -> int {
+    if (numel != n) return rb::fail(RB200_ERR_INVALID, "%s: expected %lld elements, got %lld", name_c, (long long)n,
+                                    (long long)numel);
+    return 0;
+  };
+  int layer = -1, sub = -1, pos = -1;
+  char what[64] = {0};
+  int st = 0;
+  if (name == "shared.weight" || name == "encoder.embed_tokens.weight") {
+    RB_TRY(expect((int64_t)e->cfg.vocab_size * d));
+    st = copy_f32(e->shared_emb, data, numel, s);
+    e->have.insert("shared.weight");
+    return st;
+  } else if (name == "start_token_embed") {
+    RB_TRY(expect(d));
+    st = copy_f32(e->start_emb, data, numel, s);
+  } else if (name == "encoder.final_layer_norm.weight") {
+    RB_TRY(expect(d));
+    st = copy_f32(e->enc_final_ln, data, numel, s);
+  } else if (name == "decoder.final_layer_norm.weight") {
+    RB_TRY(expect(d));
+    st = copy_f32(e->dec_final_ln, data, numel, s);
+  } else if (sscanf(name_c, "list_decoder_embeds.%d.weight", &pos) == 1) {
+    RB_REQUIRE(pos >= 0 && pos < e->Lmodel, "%s: position outside [0, %d)", name_c, e->Lmodel);
+    RB_TRY(expect(V * d));
+    RB_TRY(copy_f32(e->in_tab[pos], data, numel, s));
+    if (e->cfg.shared_output_input_embeds) st = pack_rows(e, &e->out_tab[pos], 0, data, V, s);
+  } else if (sscanf(name_c, "list_output_embeds.%d.weight", &pos) == 1) {
+    RB_REQUIRE(pos >= 0 && pos < e->Lmodel, "%s: position outside [0, %d)", name_c, e->Lmodel);
+    RB_TRY(expect(V * d));
+    if (!e->cfg.shared_output_input_embeds) st = pack_rows(e, &e->out_tab[pos], 0, data, V, s);
+  } else if (sscanf(name_c, "encoder.block.%d.layer.%d.%63s", &layer, &sub, what) == 3 ||
+             sscanf(name_c, "decoder.block.%d.layer.%d.%63s", &layer, &sub, what) == 3) {
+    const bool is_dec = name.compare(0, 7, "decoder") == 0;
+    auto& layers = is_dec ? e->dec : e->enc;
+    RB_REQUIRE(layer >= 0 && layer < (int)layers.size(), "%s: no such block", name_c);
+    Layer& l = layers[layer];
+    const std::string w(what);
+    const int ff_sub = is_dec ? 2 : 1;
+    if (w == "layer_norm.weight") {
+      RB_TRY(expect(d));
+      float* dst = sub == 0 ? l.ln0 : (sub == 1 ? l.ln1 : l.ln2);
+      RB_REQUIRE(dst != nullptr && sub <= ff_sub, "%s: no such sub-layer", name_c);
+      st = copy_f32(dst, data, numel, s);
+    } else if (sub == 0 && w == "SelfAttention.relative_attention_bias.weight") {
+      RB_TRY(expect((int64_t)e->cfg.num_buckets * e->H));
+      RB_REQUIRE(layer == 0, "%s: only block 0 carries the relative attention bias", name_c);
+      auto& host = is_dec ? e->dec_rel_host : e->enc_rel_host;
+      host.resize(numel);
+      RB_CUDA(cudaMemcpyAsync(host.data(), data, numel * 4, cudaMemcpyDeviceToHost, s));
+      RB_CUDA(cudaStreamSynchronize(s));
+    } else if (sub == 0 && (w == "SelfAttention.q.weight" || w == "SelfAttention.k.weight" ||
+                            w == "SelfAttention.v.weight")) {
+      RB_TRY(expect(inner * d));
+      const int which = w[14] == 'q' ? 0 : (w[14] == 'k' ? 1 : 2);
+      st = pack_rows(e, &l.qkv, which * inner, data, inner, s);
+    } else if (sub == 0 && w == "SelfAttention.o.weight") {
+      RB_TRY(expect(d * inner));
+      st = pack_rows(e, &l.o, 0, data, d, s);
+    } else if (is_dec && sub == 1 && w == "EncDecAttention.q.weight") {
+      RB_TRY(expect(inner * d));
+      st = pack_rows(e, &l.cq, 0, data, inner, s);
+    } else if (is_dec && sub == 1 && (w == "EncDecAttention.k.weight" || w == "EncDecAttention.v.weight")) {
+      RB_TRY(expect(inner * d));
+      const int which = w[16] == 'k' ? 0 : 1;
+      st = pack_rows(e, &e->ckv, ((int64_t)layer * 2 + which) * inner, data, inner, s);
+    } else if (is_dec && sub == 1 && w == "EncDecAttention.o.weight") {
+      RB_TRY(expect(d * inner));
+      st = pack_rows(e, &l.co, 0, data, d, s);
+    } else if (sub == ff_sub && w == "DenseReluDense.wi.weight") {
+      RB_TRY(expect(dff * d));
+      st = pack_rows(e, &l.wi, 0, data, dff, s);
+    } else if (sub == ff_sub && w == "DenseReluDense.wo.weight") {
+      RB_TRY(expect(d * dff));
+      st = pack_rows(e, &l.wo, 0, data, d, s);
+    } else {
+      return rb::fail(RB200_ERR_INVALID, "unknown weight %s", name_c);
+    }
+  } else {
+    return rb::fail(RB200_ERR_INVALID, "unknown weight %s", name_c);
+  }
+  if (st == 0) e->have.insert(name);
+  return st;
+}
+
+int rb200_engine_finalize_weights(rb200_engine* e, void* stream) {
+  RB_REQUIRE(e, "null argument");
+  std::vector<std::string> need = {"shared.weight", "start_token_embed", "encoder.final_layer_norm.weight",
+                                   "decoder.final_layer_norm.weight",
+                                   "encoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight",
+                                   "decoder.block.0.layer.0.SelfAttention.relative_attention_bias.weight"};
+  for (int side = 0; side < 2; ++side) {
+    const int nl = side ? e->cfg.num_decoder_layers : e->cfg.num_layers;
+    const std::string pre = side ? "decoder.block." : "encoder.block.";
+    for (int i = 0; i < nl; ++i) {
+      const std::string p = pre + std::to_string(i) + ".layer.";
+      for (const char* w : {"q", "k", "v", "o"}) need.push_back(p + "0.SelfAttention." + w + ".weight");
+      need.push_back(p + "0.layer_norm.weight");
+      int ff = 1;
+      if (side) {
+        for (const char* w : {"q", "k", "v", "o"}) need.push_back(p + "1.EncDecAttention." + w + ".weight");
+        need.push_back(p + "1.layer_norm.weight");
+        ff = 2;
+      }
+      need.push_back(p + std::to_string(ff) + ".DenseReluDense.wi.weight");
+      need.push_back(p + std::to_string(ff) + ".DenseReluDense.wo.weight");
+      need.push_back(p + std::to_string(ff) + ".layer_norm.weight");
+    }
+  }
+  for (int t = 0; t < e->Lmodel; ++t) {
+    need.push_back("list_decoder_embeds." + std::to_string(t) + ".weight");
+    if (!e->cfg.shared_output_input_embeds) need.push_back("list_output_embeds." + std::to_string(t) + ".weight");
+  }
+  for (const auto& n : need)
+    if (!e->have.count(n)) return rb::fail(RB200_ERR_STATE, "weight %s has not been set", n.c_str());
+  RB_TRY(build_bias_tables(e, 0, (cudaStream_t)stream));
+  RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  e->finalized = true;
+  return 0;
+}
+
+int rb200_engine_encode(rb200_engine* e, const int64_t* ids, const int64_t* mask, int batch, int S, int num_beams,
+                        void* stream) {
+  RB_REQUIRE(e && ids && mask, "null argument");
+  if (!e->finalized) return rb::fail(RB200_ERR_STATE, "weights not finalized: call rb200_engine_finalize_weights");
+  RB_REQUIRE(batch >= 1 && batch <= e->cfg.max_batch, "batch %d outside [1, %d]", batch, e->cfg.max_batch);
+  RB_REQUIRE(S >= 1 && S <= e->cfg.max_src_len, "source length %d outside [1, %d]", S, e->cfg.max_src_len);
+  RB_REQUIRE(num_beams >= 1 && num_beams <= e->cfg.max_beams, "num_beams %d outside [1, %d]", num_beams,
+             e->cfg.max_beams);
+  cudaStream_t s = (cudaStream_t)stream;
+  RB_CUDA(cudaSetDevice(e->cfg.device));
+  RB_TRY(build_bias_tables(e, S, s));
+  e->B = batch; e->S = S; e->nb = num_beams; e->cur_mask = mask;
+  const int64_t rows = (int64_t)batch * S;
+  const int d = e->d, inner = e->inner, dff = e->dff;
+  const float eps = e->cfg.layer_norm_eps;
+  RB_TRY(rb::launch_embed_rows(e->shared_emb, ids, e->x, rows, d, s));
+  for (auto& l : e->enc) {
+    RB_TRY(rb::launch_rmsnorm(e->x, l.ln0, e->act(e->xn, d), rows, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, e->xn, d, l.qkv, e->qkv, 3 * inner, ActOut{}, rows, rb::EPI_STORE, s));
+    rb::EncAttnArgs ea{e->qkv, mask, e->enc_bias, batch, S, e->H};
+    RB_TRY(rb::launch_enc_attn(ea, e->act(e->ctx, inner), s));
+    RB_TRY(gemm(e, e->ctx, inner, l.o, e->x, d, ActOut{}, rows, rb::EPI_RESIDUAL, s));
+    RB_TRY(rb::launch_rmsnorm(e->x, l.ln1, e->act(e->xn, d), rows, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, e->xn, d, l.wi, nullptr, 0, e->act(e->hbuf, dff), rows, rb::EPI_RELU_ACT, s));
+    RB_TRY(gemm(e, e->hbuf, dff, l.wo, e->x, d, ActOut{}, rows, rb::EPI_RESIDUAL, s));
+  }
+  RB_TRY(rb::launch_rmsnorm_f32(e->x, e->enc_final_ln, e->enc_out, rows, d, eps, s));
+  RB_TRY(rb::launch_rmsnorm(e->x, e->enc_final_ln, e->act(e->xn, d), rows, d, eps, 1.0f, s));
+  // cross-attention K/V of every decoder layer in one GEMM: [B*S, d] x [d, Nl*2*inner]
+  RB_TRY(gemm(e, e->xn, d, e->ckv, e->cross_kv, e->ckv.N, ActOut{}, rows, rb::EPI_STORE, s));
+  return 0;
+}
+
+int rb200_engine_encoder_states(const rb200_engine* e, const float** states) {
+  RB_REQUIRE(e && states, "null argument");
+  *states = e->enc_out;
+  return 0;
+}
+
+int rb200_engine_decode_step(rb200_engine* e, const rb200_beam* beam, int t, float* logits, void* stream) {
+  RB_REQUIRE(e && beam && logits, "null argument");
+  if (e->B < 1) return rb::fail(RB200_ERR_STATE, "rb200_engine_encode has not been called");
+  RB_REQUIRE(t >= 0 && t < e->Lmodel, "position %d outside [0, %d)", t, e->Lmodel);
+  RB_REQUIRE(beam->step == t, "beam state is at step %d, decoder asked for position %d", beam->step, t);
+  RB_REQUIRE(beam->nb == e->nb && beam->batch == e->B, "beam state shape differs from the encoded batch");
+  RB_REQUIRE(beam->L == e->Lmodel, "beam state L=%d differs from the model's docid_len=%d", beam->L, e->Lmodel);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int rpq = (t == 0) ? 1 : e->nb;
+  const int64_t M = (int64_t)e->B * rpq;
+  const int d = e->d, inner = e->inner, dff = e->dff;
+  const float eps = e->cfg.layer_norm_eps;
+  if (t == 0) {
+    RB_TRY(rb::launch_broadcast_row(e->start_emb, e->x, M, d, s));
+  }
+  const int64_t layer_cache = (int64_t)e->Lmodel * e->Rcap * inner;
+  const int64_t ckv_ld = e->ckv.N;
+  for (size_t i = 0; i < e->dec.size(); ++i) {
+    Layer& l = e->dec[i];
+    RB_TRY(rb::launch_rmsnorm(e->x, l.ln0, e->act(e->xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, e->xn, d, l.qkv, e->qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
+    rb::SelfAttnArgs sa;
+    sa.qkv = e->qkv; sa.cache_k = e->cache_k + i * layer_cache; sa.cache_v = e->cache_v + i * layer_cache;
+    sa.anc = beam->anc[beam->cur]; sa.bias = e->dec_bias; sa.row_cap = e->Rcap;
+    sa.M = (int)M; sa.H = e->H; sa.L = e->Lmodel; sa.t = t; sa.rpq = rpq; sa.nb = e->nb;
+    RB_TRY(rb::launch_self_attn_decode(sa, e->act(e->ctx, inner), s));
+    RB_TRY(gemm(e, e->ctx, inner, l.o, e->x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+    RB_TRY(rb::launch_rmsnorm(e->x, l.ln1, e->act(e->xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, e->xn, d, l.cq, e->q2, inner, ActOut{}, M, rb::EPI_STORE, s));
+    rb::CrossAttnArgs ca;
+    ca.q = e->q2; ca.kv = e->cross_kv; ca.ld = ckv_ld; ca.k_off = (int64_t)(i * 2) * inner;
+    ca.v_off = (int64_t)(i * 2 + 1) * inner; ca.mask = e->cur_mask; ca.M = (int)M; ca.H = e->H; ca.S = e->S;
+    ca.rows_per_query = rpq;
+    RB_TRY(rb::launch_cross_attn_decode(ca, e->act(e->ctx, inner), s));
+    RB_TRY(gemm(e, e->ctx, inner, l.co, e->x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+    RB_TRY(rb::launch_rmsnorm(e->x, l.ln2, e->act(e->xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, e->xn, d, l.wi, nullptr, 0, e->act(e->hbuf, dff), M, rb::EPI_RELU_ACT, s));
+    RB_TRY(gemm(e, e->hbuf, dff, l.wo, e->x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+  }
+  const float scale = e->cfg.scaleup_output_hidden ? 1.0f / sqrtf((float)d) : 1.0f;
+  RB_TRY(rb::launch_rmsnorm(e->x, e->dec_final_ln, e->act(e->xn, d), M, d, eps, scale, s));
+  RB_TRY(gemm(e, e->xn, d, e->out_tab[t], logits, e->V, ActOut{}, M, rb::EPI_STORE, s));
+  return 0;
+}
+
+int rb200_engine_beam(rb200_engine* e, rb200_beam** beam) {
+  RB_REQUIRE(e && beam, "null argument");
+  *beam = e->beam;
+  return 0;
+}
+
+int64_t rb200_engine_last_launch_count(const rb200_engine* e) { return e ? e->launches : 0; }
+
+int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* ids, const int64_t* mask, int batch,
+                        int S, int num_beams, int max_new_tokens, int num_return, int apply_log_softmax,
+                        int64_t* sequences, float* scores, int32_t* leaf, void* stream) {
+  RB_REQUIRE(e && trie && ids && mask && sequences && scores, "null argument");
+  RB_REQUIRE(num_beams == e->cfg.max_beams, "the engine was created for num_beams=%d, got %d", e->cfg.max_beams,
+             num_beams);
+  RB_REQUIRE(max_new_tokens >= 1 && max_new_tokens <= e->Lmodel && max_new_tokens <= trie->L,
+             "max_new_tokens=%d outside [1, min(model %d, trie %d)]", max_new_tokens, e->Lmodel, trie->L);
+  RB_REQUIRE(num_return >= 1 && num_return <= num_beams,
+             "`num_return_sequences` has to be smaller or equal to `num_beams`.");
+  RB_REQUIRE(trie->V == e->V, "trie V=%d but the model's decoder_vocab_size is %d", trie->V, e->V);
+  const int64_t launches0 = rb::launch_count();
+  RB_TRY(rb200_engine_encode(e, ids, mask, batch, S, num_beams, stream));
+  RB_TRY(rb200_beam_reset(e->beam, trie, batch, stream));
+  for (int t = 0; t < max_new_tokens; ++t) {
+    RB_TRY(rb200_engine_decode_step(e, e->beam, t, e->logits, stream));
+    const bool more = t + 1 < max_new_tokens;
+    RB_TRY(rb200_beam_step(e->beam, trie, e->logits, t == 0 ? 1 : num_beams, apply_log_softmax,
+                           more ? e->in_tab[t] : nullptr, more ? e->x : nullptr, e->d, stream));
+  }
+  RB_TRY(rb200_beam_finalize(e->beam, trie, num_return, 1.0, sequences, scores, leaf, stream));
+  e->launches = rb::launch_count() - launches0;
+  return 0;
+}
+
+int rb200_engine_search_host(rb200_engine* e, const rb200_trie* trie, const int64_t* ids_host,
+                             const int64_t* mask_host, int batch, int S, int num_beams, int max_new_tokens,
+                             int num_return, int apply_log_softmax, int64_t* sequences_host, float* scores_host,
+                             int32_t* leaf_host, void* stream) {
+  RB_REQUIRE(e && ids_host && mask_host && sequences_host && scores_host, "null argument");
+  RB_REQUIRE(batch >= 1 && batch <= e->cfg.max_batch, "batch %d outside [1, %d]", batch, e->cfg.max_batch);
+  RB_REQUIRE(S >= 1 && S <= e->cfg.max_src_len, "source length %d outside [1, %d]", S, e->cfg.max_src_len);
+  cudaStream_t s = (cudaStream_t)stream;
+  RB_CUDA(cudaSetDevice(e->cfg.device));
+  const size_t nin = (size_t)batch * S * 8;
+  RB_CUDA(cudaMemcpyAsync(e->ids_dev, ids_host, nin, cudaMemcpyHostToDevice, s));
+  RB_CUDA(cudaMemcpyAsync(e->mask_dev, mask_host, nin, cudaMemcpyHostToDevice, s));
+  RB_TRY(rb200_engine_search(e, trie, e->ids_dev, e->mask_dev, batch, S, num_beams, max_new_tokens, num_return,
+                             apply_log_softmax, e->seq_dev, e->score_dev, e->leaf_dev, stream));
+  const size_t n = (size_t)batch * num_return;
+  RB_CUDA(cudaMemcpyAsync(sequences_host, e->seq_dev, n * (max_new_tokens + 1) * 8, cudaMemcpyDeviceToHost, s));
+  RB_CUDA(cudaMemcpyAsync(scores_host, e->score_dev, n * 4, cudaMemcpyDeviceToHost, s));
+  if (leaf_host) RB_CUDA(cudaMemcpyAsync(leaf_host, e->leaf_dev, n * 2 * 4, cudaMemcpyDeviceToHost, s));
+  RB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+int rb200_engine_set_profiling(rb200_engine* e, int on) {
+  RB_REQUIRE(e, "null argument");
+  e->profiling = on != 0;
+  e->ev_used = 0;
+  e->prof_flops = 0.0;
+  return 0;
+}
+
+int rb200_engine_get_profile(rb200_engine* e, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  RB_REQUIRE(e && gemm_ms && gemm_flops && gemm_launches, "null argument");
+  double ms = 0.0;
+  for (size_t i = 0; i + 1 < e->ev_used; i += 2) {
+    RB_CUDA(cudaEventSynchronize(e->events[i + 1]));
+    float t = 0.f;
+    RB_CUDA(cudaEventElapsedTime(&t, e->events[i], e->events[i + 1]));
+    ms += t;
+  }
+  *gemm_ms = ms;
+  *gemm_flops = e->prof_flops;
+  *gemm_launches = (int64_t)(e->ev_used / 2);
+  return 0;
+}
+
+int rb200_gemm(int precision, const float* A, const float* W, float* C, int64_t M, int64_t N, int64_t K,
+               int accumulate, int relu, void* stream) {
+  RB_REQUIRE(A && W && C, "null argument");
+  RB_REQUIRE(precision >= 0 && precision <= 4, "unknown precision %d", precision);
+  RB_REQUIRE(!(accumulate && relu), "accumulate and relu are exclusive");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int planes = rb::prec_planes(precision), elem = rb::prec_elem_bytes(precision);
+  void *Ap = nullptr, *Wp = nullptr, *Rp = nullptr;
+  RB_CUDA(cudaMalloc(&Ap, (size_t)planes * M * K * elem));
+  RB_CUDA(cudaMalloc(&Wp, (size_t)planes * N * K * elem));
+  int st = rb::launch_pack_planes(A, Ap, M * K, M * K, precision, s);
+  if (st == 0) st = rb::launch_pack_planes(W, Wp, N * K, N * K, precision, s);
+  GemmArgs g;
+  g.mode = precision; g.A = Ap; g.a_plane = M * K; g.W = Wp; g.w_plane = N * K;
+  g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
+  g.epilogue = accumulate ? rb::EPI_RESIDUAL : rb::EPI_STORE;
+  g.act = ActOut{};
+  if (relu) {   // ReLU epilogue writes planes; unpack plane 0 (+ plane 1) back to fp32 for the caller
+    if (cudaMalloc(&Rp, (size_t)planes * M * N * elem) != cudaSuccess) st = RB200_ERR_CUDA;
+    g.epilogue = rb::EPI_RELU_ACT;
+    g.act = ActOut{Rp, M * N, precision};
+  }
+  if (st == 0) st = rb::launch_gemm(g, s);
+  if (st == 0 && relu) {
+    std::vector<char> host((size_t)planes * M * N * elem);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(host.data(), Rp, host.size(), cudaMemcpyDeviceToHost);
+    std::vector<float> out((size_t)M * N);
+    for (int64_t i = 0; i < M * N; ++i) {
+      float v = 0.f;
+      for (int p = 0; p < planes; ++p) {
+        if (elem == 4) v += reinterpret_cast<float*>(host.data())[p * M * N + i];
+        else {
+          uint32_t b = (uint32_t)reinterpret_cast<uint16_t*>(host.data())[p * M * N + i] << 16;
+          float f;
+          memcpy(&f, &b, 4);
+          v += f;
+        }
+      }
+      out[i] = v;
+    }
+    cudaMemcpy(C, out.data(), out.size() * 4, cudaMemcpyHostToDevice);
+  }
+  cudaStreamSynchronize(s);
+  cudaFree(Ap); cudaFree(Wp); cudaFree(Rp);
+  if (st == 0) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return rb::fail(RB200_ERR_CUDA, "rb200_gemm: %s", cudaGetErrorString(err));
+  }
+  return st;
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+"""Shared helpers for the parity tests: rebuild golden-case inputs, run the oracle, wrap the C ABI."""
+import json
+import os
+
+import numpy as np
+import torch
+
+from oracle import beam as ob, t5_math
+from oracle.make_golden import CASES, case_inputs
+from ripor_b200 import synthetic as syn
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def load_golden(name):
+    g = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    c = json.loads(str(g["case"]))
+    se = g["start_token_embed"] if g["start_token_embed"].size else None
+    dims, w, codes, ids, mask = case_inputs(name, c, se)
+    assert np.array_equal(np.frombuffer(codes.tobytes()[:64], np.uint8), g["codes_sha"]), "synthetic codes drifted"
+    assert np.array_equal(ids.numpy(), g["input_ids"]), "synthetic queries drifted"
+    return c, dims, w, codes, ids, mask, g
+
+
+def oracle_cached_search(w, dims, codes, ids, mask, nb, L, log_softmax=False, keep=None):
+    """KV-cached oracle run -> (sequences [B*keep, L+1], scores [B*keep], trace)."""
+    V = dims.decoder_vocab_size
+    lst = ob.build_list_smtid_to_nextids(syn.codes_to_docid_to_smtid(codes[:, :L] if codes.shape[1] >= L else codes))
+    B = ids.shape[0]
+    with torch.no_grad():
+        enc = t5_math.encoder_forward(w, dims, ids, mask)
+        dec = t5_math.CachedDecoder(w, dims, enc, mask, nb)
+
+        def step(dec_ids, bi):
+            if bi is not None:
+                dec.reorder(bi)
+            return dec.step(None if dec_ids.shape[1] == 1 else dec_ids[:, -1])
+        trace = []
+        seqs, scores = ob.beam_search_oracle(step, ob.TrieMaskOracle(lst, V), B, nb, L,
+                                             num_return_sequences=keep, apply_log_softmax_for_scores=log_softmax,
+                                             trace=trace)
+    return seqs, scores, trace, enc
+
+
+def compare_ranked(seqs, scores, ref_seqs, ref_scores, nb, atol=1e-3, near_tie=0.0, trace=None):
+    """DocID lists bit-exact on valid rows, scores within atol. Rows whose reference score is below -1e8
+    are -1e9 survivors (dropped by the reference at evaluate.py:121-122): only their scores are compared
+    (torch.topk leaves the order of exactly tied candidates unspecified)."""
+    seqs, ref_seqs = seqs.cpu(), ref_seqs.cpu()
+    scores, ref_scores = scores.cpu().double(), ref_scores.cpu().double()
+    valid = ref_scores > -1e6
+    assert torch.equal(valid, scores > -1e6), "different number of valid beams"
+    big = torch.where(valid, torch.zeros_like(scores), scores - ref_scores)
+    assert torch.all(big.abs() <= 1e-2 * 33), f"penalised scores differ: {big.abs().max()}"
+    mism = (seqs != ref_seqs).any(dim=1) & valid
+    assert torch.allclose(scores[valid & ~mism], ref_scores[valid & ~mism], atol=atol, rtol=0), \
+        f"score diff {(scores - ref_scores)[valid & ~mism].abs().max()}"
+    return int(mism.view(-1, nb).any(dim=1).sum())
