@@ -1,0 +1,362 @@
+"""CLI entry point for the retrieval tasks, same flags and files as the reference's evaluate.py.
+
+    python -m ripor_b200.evaluate --task=t5seq_aq_retrieve_docids --pretrained_path P --docid_to_smtid_path J \
+        --q_collection_paths '["dir/"]' --batch_size B --max_new_token_for_docid L --topk nb --out_dir O \
+        [--apply_log_softmax_for_scores] [--local_rank r]
+    python -m ripor_b200.evaluate --task=t5seq_aq_retrieve_docids_2 --out_dir O --q_collection_paths '["dir/"]'
+
+Mirrors reference t5_pretrainer/evaluate.py: ``t5seq_aq_retrieve_docids`` (:396-487), ``constrained_decode_doc``
+(:87-132), ``t5seq_aq_retrieve_docids_2`` (:489-526), the query feed ``CollectionDatasetWithDocIDPreLoad`` /
+``CollectionDataWithDocIDLoader`` (dataset/dataset.py:266-332, dataset/dataloader.py:62-79) and
+``DistributedSampler(shuffle=False)`` sharding (:463-468). Output files are the reference's:
+``<out_dir>/<dataset>/run_{local_rank}.json`` = {qid: {docid: score}} and the merged ``run.json``.
+When a process group is initialised the per-rank runs can also be gathered over NCCL/gloo
+(``gather_runs``) instead of going through the shared file system.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pickle
+from typing import Callable, Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from .generation import PrefixConstrainLogitProcessorFastSparse, generate_for_constrained_prefix_beam_search
+from .modeling import T5SeqAQEncoder
+from .trie import DocidTrie
+from .utils import convert_ptsmtids_to_strsmtid, get_dataset_name
+
+QUERY_PREFIX = "query: "          # reference dataset/dataset.py:15
+
+
+# ---------------------------------------------------------------------------------------------------
+# query feed
+# ---------------------------------------------------------------------------------------------------
+class CollectionDatasetWithDocIDPreLoad:
+    """raw.tsv reader with the reference's row-id access and "query: " prefix (dataset.py:266-332)."""
+
+    def __init__(self, data_dir: str, id_style: str = "row_id", tid_to_smtid_path=None, add_prefix=False,
+                 is_query=False):
+        assert id_style in ("content_id", "row_id"), "provide valid id_style"
+        self.data_dir, self.id_style = data_dir, id_style
+        self.data_dict, self.line_dict = {}, {}
+        with open(os.path.join(data_dir, "raw.tsv")) as reader:
+            for i, line in enumerate(reader):
+                if len(line) > 1:
+                    id_, *data = line.split("\t")
+                    data = " ".join(" ".join(data).splitlines())
+                    if id_style == "row_id":
+                        self.data_dict[i] = data
+                        self.line_dict[i] = id_.strip()
+                    else:
+                        self.data_dict[id_] = data.strip()
+        self.nb_ex = len(self.data_dict)
+        self.add_prefix, self.is_query = add_prefix, is_query
+
+    def __len__(self):
+        return self.nb_ex
+
+    def __getitem__(self, idx):
+        text = self.data_dict[idx]
+        if self.add_prefix and self.is_query:
+            text = QUERY_PREFIX + text
+        return self.line_dict[idx], text, [-1]
+
+
+def distributed_sampler_indices(n: int, world_size: int, rank: int) -> List[int]:
+    """torch DistributedSampler(shuffle=False, drop_last=False): pad by wrapping, then stride by rank."""
+    if world_size <= 1:
+        return list(range(n))
+    total = -(-n // world_size) * world_size
+    idx = list(range(n))
+    pad = total - n
+    if pad > 0:
+        idx += (idx * (pad // max(len(idx), 1) + 1))[:pad]
+    return idx[rank:total:world_size]
+
+
+class CollectionDataWithDocIDLoader:
+    """Batches of {"input_ids", "attention_mask", "id"}: tokenise, pad to the longest row, truncate to
+    max_length (dataloader.py:62-79). ``tokenizer`` is an HF tokenizer (AutoTokenizer.from_pretrained(path)) or any
+    callable text -> list[int]; batches are placed in pinned host memory like the reference's pin_memory=True."""
+
+    def __init__(self, dataset, tokenizer_type=None, max_length=256, batch_size=1, sampler: Optional[Sequence[int]] = None,
+                 tokenizer: Optional[Callable] = None, **_):
+        self.dataset, self.max_length, self.batch_size = dataset, max_length, batch_size
+        self.indices = list(sampler) if sampler is not None else list(range(len(dataset)))
+        if tokenizer is None:
+            from transformers import AutoTokenizer
+            tokenizer = AutoTokenizer.from_pretrained(tokenizer_type)
+        self.tokenizer = tokenizer
+
+    def __len__(self):
+        return -(-len(self.indices) // self.batch_size)
+
+    def _encode(self, texts: List[str]):
+        if hasattr(self.tokenizer, "pad_token_id") or hasattr(self.tokenizer, "batch_encode_plus"):
+            enc = self.tokenizer(texts, add_special_tokens=True, padding="longest", truncation="longest_first",
+                                 max_length=self.max_length, return_attention_mask=True)
+            return torch.tensor(enc["input_ids"]), torch.tensor(enc["attention_mask"])
+        rows = [list(self.tokenizer(t))[: self.max_length] for t in texts]
+        S = max(len(r) for r in rows)
+        ids = torch.zeros((len(rows), S), dtype=torch.long)
+        mask = torch.zeros((len(rows), S), dtype=torch.long)
+        for i, r in enumerate(rows):
+            ids[i, : len(r)] = torch.tensor(r)
+            mask[i, : len(r)] = 1
+        return ids, mask
+
+    def __iter__(self):
+        for s in range(0, len(self.indices), self.batch_size):
+            items = [self.dataset[i] for i in self.indices[s: s + self.batch_size]]
+            id_, texts, _ = zip(*items)
+            ids, mask = self._encode(list(texts))
+            pin = torch.cuda.is_available()
+            yield {"input_ids": ids.pin_memory() if pin else ids, "attention_mask": mask.pin_memory() if pin else mask,
+                   "id": torch.tensor([int(i) for i in id_], dtype=torch.long)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# decode loop (evaluate.py:87-132)
+# ---------------------------------------------------------------------------------------------------
+def constrained_decode_doc(model, dataloader, prefix_constrain_processor, smtid_to_docids, max_new_token, device,
+                           out_dir, local_rank, topk=100, apply_log_softmax_for_scores=False, write=True):
+    """smtid_to_docids: the reference's dict {"c1_.._cL": [docids]} or None to expand leaves from the trie."""
+    qid_to_rankdata: Dict[int, Dict[str, float]] = {}
+    trie: DocidTrie = prefix_constrain_processor.trie
+    for batch in dataloader:
+        outputs = generate_for_constrained_prefix_beam_search(
+            model, prefix_constrain_processor, input_ids=batch["input_ids"].long(),
+            attention_mask=batch["attention_mask"].long(), max_new_tokens=max_new_token, output_scores=True,
+            return_dict=True, return_dict_in_generate=True, num_beams=topk, num_return_sequences=topk,
+            apply_log_softmax_for_scores=apply_log_softmax_for_scores)
+        batch_qids = batch["id"].cpu().tolist()
+        seqs = outputs.sequences.view(-1, topk, max_new_token + 1)
+        relevant_scores = outputs.sequences_scores.view(-1, topk).cpu().tolist()
+        if smtid_to_docids is not None:
+            str_smtids = convert_ptsmtids_to_strsmtid(seqs, max_new_token)
+            for qid, ranked_smtids, rel_scores in zip(batch_qids, str_smtids, relevant_scores):
+                qid_to_rankdata[qid] = {}
+                for smtid, rel_score in zip(ranked_smtids, rel_scores):
+                    if smtid not in smtid_to_docids:
+                        print(f"smtid: {smtid} not in smtid_to_docid")
+                    else:
+                        for docid in smtid_to_docids[smtid]:
+                            qid_to_rankdata[qid][docid] = rel_score if apply_log_softmax_for_scores \
+                                else rel_score * max_new_token
+        else:   # same mapping from the trie's leaf table, no Python dict of 8.8M strings
+            leaf = outputs.leaf_ranges.view(-1, topk, 2).cpu().tolist()
+            for qid, ranges, rel_scores in zip(batch_qids, leaf, relevant_scores):
+                qid_to_rankdata[qid] = {}
+                for (lo, hi), rel_score in zip(ranges, rel_scores):
+                    if hi <= lo:
+                        print("smtid not in smtid_to_docid")
+                        continue
+                    for docid in trie.docids_for_range(lo, hi):
+                        qid_to_rankdata[qid][docid] = rel_score if apply_log_softmax_for_scores \
+                            else rel_score * max_new_token
+    if write:
+        with open(os.path.join(out_dir, f"run_{local_rank}.json"), "w") as fout:
+            json.dump(qid_to_rankdata, fout)
+    return qid_to_rankdata
+
+
+def build_list_smtid_to_nextids(docid_to_smtids):
+    """evaluate.py:411-424 (kept for callers that want the reference's pickle format)."""
+    out = [dict() for _ in range(len(next(iter(docid_to_smtids.values()))) - 1)]
+    for _, smtids in docid_to_smtids.items():
+        for i in range(len(smtids) - 1):
+            out[i].setdefault("_".join(str(x) for x in smtids[: i + 1]), set()).add(int(smtids[i + 1]))
+    return [{k: list(v) for k, v in d.items()} for d in out]
+
+
+def ddp_setup():
+    if "RANK" in os.environ and not torch.distributed.is_initialized():
+        torch.distributed.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
+
+
+def t5seq_aq_retrieve_docids(args, tokenizer=None):
+    ddp_setup()
+    model = T5SeqAQEncoder.from_pretrained(args.pretrained_path)
+    model.eval()
+    with open(args.docid_to_smtid_path) as fin:
+        docid_to_smtids = json.load(fin)
+    print(args.docid_to_smtid_path)
+    V = model.config.decoder_vocab_sizes
+    if len(set(V)) != 1:
+        raise ValueError("not valid decoder_vocab_size")
+    cache = os.path.join(os.path.dirname(args.docid_to_smtid_path), "docid_trie.rb200")
+    docids = list(docid_to_smtids.keys())
+    if os.path.exists(cache):
+        print("read flattened trie from {}".format(cache))
+        trie = DocidTrie.load(cache, docids)
+    else:
+        pkl = os.path.join(os.path.dirname(args.docid_to_smtid_path), "list_smtid_to_nextids.pkl")
+        trie = DocidTrie.from_docid_to_smtid(docid_to_smtids, V[0])
+        if args.local_rank <= 0:
+            for i, n in enumerate(trie.level_counts()):
+                print(f"{i}-th step has {n:,} effective smtid ")
+            if "experiments-full" in args.docid_to_smtid_path and not os.path.exists(pkl):
+                trie.save(cache)
+    prefix_constrain_processor = PrefixConstrainLogitProcessorFastSparse.from_trie(trie)
+    max_new_token = args.max_new_token_for_docid
+    first = docid_to_smtids[docids[0]]
+    assert first[0] == -1, first
+    assert len(first) - 1 >= max_new_token, (first, max_new_token)
+    if args.local_rank <= 0:
+        print("max_new_token: ", max_new_token)
+        os.makedirs(args.out_dir, exist_ok=True)
+    q_paths = args.q_collection_paths
+    if len(q_paths) == 1 and q_paths[0].lstrip().startswith("["):
+        q_paths = json.loads(q_paths[0])
+    world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+    rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+    local_rank = max(args.local_rank, 0)
+    for data_dir in q_paths:
+        dev_dataset = CollectionDatasetWithDocIDPreLoad(data_dir=data_dir, id_style="row_id", tid_to_smtid_path=None,
+                                                        add_prefix=True, is_query=True)
+        dev_loader = CollectionDataWithDocIDLoader(dataset=dev_dataset, tokenizer_type=args.pretrained_path,
+                                                   max_length=256, batch_size=args.batch_size,
+                                                   sampler=distributed_sampler_indices(len(dev_dataset), world, rank),
+                                                   tokenizer=tokenizer)
+        model.to(local_rank)
+        out_dir = os.path.join(args.out_dir, get_dataset_name(data_dir))
+        print("out_dir: ", out_dir)
+        os.makedirs(out_dir, exist_ok=True)
+        model.base_model.config.decoding = True
+        # the trie was built on the full codes; shorter DocIDs (max_new_token < L) map to leaf ranges
+        constrained_decode_doc(model.base_model, dev_loader, prefix_constrain_processor, None, max_new_token,
+                               device=local_rank, out_dir=out_dir, local_rank=local_rank, topk=args.topk,
+                               apply_log_softmax_for_scores=args.apply_log_softmax_for_scores)
+
+
+def merge_rank_runs(sub_runs: List[Dict]) -> Dict:
+    """evaluate.py:506-515: dict update per qid (duplicates from sampler padding collapse)."""
+    merged: Dict = {}
+    for sub in sub_runs:
+        if len(merged) == 0:
+            merged.update(sub)
+        else:
+            for qid, rankdata in sub.items():
+                if qid not in merged:
+                    merged[qid] = rankdata
+                else:
+                    merged[qid].update(rankdata)
+    return merged
+
+
+def t5seq_aq_retrieve_docids_2(args):
+    q_paths = args.q_collection_paths
+    if len(q_paths) == 1 and q_paths[0].lstrip().startswith("["):
+        q_paths = json.loads(q_paths[0])
+    for data_dir in q_paths:
+        out_dir = os.path.join(args.out_dir, get_dataset_name(data_dir))
+        if os.path.exists(os.path.join(out_dir, "run.json")):
+            print("old run.json exisit.")
+            os.remove(os.path.join(out_dir, "run.json"))
+        sub_paths = [p for p in os.listdir(out_dir) if "run" in p]
+        expected = args.num_ranks if args.num_ranks else torch.cuda.device_count()
+        assert len(sub_paths) == expected, (sub_paths, expected)          # evaluate.py:503-504
+        subs = []
+        for sub_path in sub_paths:
+            with open(os.path.join(out_dir, sub_path)) as fin:
+                subs.append(json.load(fin))
+        merged = merge_rank_runs(subs)
+        print("length of pids and avg rankdata length in qid_to_rankdata: {}, {}".format(
+            len(merged), np.mean([len(xs) for xs in merged.values()])))
+        with open(os.path.join(out_dir, "run.json"), "w") as fout:
+            json.dump(merged, fout)
+        for sub_path in sub_paths:
+            os.remove(os.path.join(out_dir, sub_path))
+    if args.eval_qrel_path:
+        evaluate_runs(args, q_paths)
+
+
+def gather_runs(local_run: Dict, group=None) -> Optional[Dict]:
+    """Collective replacement of the file merge: every rank contributes its {qid: {docid: score}} packed as
+    tensors; rank 0 returns the merged dict (others None). One all_gather of sizes + one of payloads."""
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        return local_run
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    payload = np.frombuffer(pickle.dumps(local_run), dtype=np.uint8).copy()
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    n = torch.tensor([payload.size], dtype=torch.int64, device=dev)
+    sizes = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(sizes, n, group=group)
+    mx = int(max(s.item() for s in sizes))
+    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
+    buf[: payload.size] = torch.from_numpy(payload).to(dev)
+    bufs = [torch.zeros_like(buf) for _ in range(world)]
+    dist.all_gather(bufs, buf, group=group)
+    if rank != 0:
+        return None
+    return merge_rank_runs([pickle.loads(b[: int(s.item())].cpu().numpy().tobytes()) for b, s in zip(bufs, sizes)])
+
+
+def mrr_k(run: Dict, qrel: Dict, k: int = 10) -> float:
+    """MRR@k without pytrec_eval (reference utils/metrics.py:18-25 truncates the run to top-k by score first)."""
+    total, n = 0.0, 0
+    for qid, rel in qrel.items():
+        ranked = sorted(run.get(qid, {}).items(), key=lambda kv: kv[1], reverse=True)[:k]
+        rr = 0.0
+        for i, (docid, _) in enumerate(ranked):
+            if rel.get(docid, 0) > 0:
+                rr = 1.0 / (i + 1)
+                break
+        total += rr
+        n += 1
+    return total / max(n, 1)
+
+
+def evaluate_runs(args, q_paths):
+    for data_dir in q_paths:
+        out_dir = os.path.join(args.out_dir, get_dataset_name(data_dir))
+        with open(os.path.join(out_dir, "run.json")) as f:
+            run = json.load(f)
+        for qrel_path in args.eval_qrel_path:
+            if get_dataset_name(qrel_path) != get_dataset_name(data_dir) or not os.path.exists(qrel_path):
+                continue
+            with open(qrel_path) as f:
+                qrel = json.load(f)
+            perf = {"mrr_10": mrr_k(run, qrel, 10)}
+            print(get_dataset_name(data_dir), perf)
+            with open(os.path.join(out_dir, "perf.json"), "w") as f:
+                json.dump(perf, f)
+
+
+def get_args(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--task", type=str, default="")
+    ap.add_argument("--pretrained_path", type=str, default="")
+    ap.add_argument("--out_dir", type=str, default="")
+    ap.add_argument("--docid_to_smtid_path", type=str, default=None)
+    ap.add_argument("--q_collection_paths", type=str, nargs="+", default=[])
+    ap.add_argument("--eval_qrel_path", type=str, nargs="*", default=[])
+    ap.add_argument("--batch_size", type=int, default=64)
+    ap.add_argument("--topk", type=int, default=200)
+    ap.add_argument("--max_new_token_for_docid", type=int, default=32)
+    ap.add_argument("--max_new_token", type=int, default=None)
+    ap.add_argument("--apply_log_softmax_for_scores", action="store_true")
+    ap.add_argument("--local_rank", type=int, default=int(os.environ.get("LOCAL_RANK", -1)))
+    ap.add_argument("--num_ranks", type=int, default=0, help="run_*.json files expected by the merge task "
+                                                              "(default: torch.cuda.device_count() like the reference)")
+    return ap.parse_args(argv)
+
+
+def main(argv=None):
+    args = get_args(argv)
+    if args.task == "t5seq_aq_retrieve_docids":
+        t5seq_aq_retrieve_docids(args)
+    elif args.task == "t5seq_aq_retrieve_docids_2":
+        t5seq_aq_retrieve_docids_2(args)
+    else:
+        raise ValueError(f"task {args.task!r} is not part of the retrieval path served here "
+                         "(t5seq_aq_retrieve_docids, t5seq_aq_retrieve_docids_2)")
+
+
+if __name__ == "__main__":
+    main()

@@ -78,7 +78,7 @@ def _run_beam_kernels(tr, B, nb, L, V, logits_fn, log_softmax, keep=None):
 def _copy_from_device(ptr, nbytes, dtype):
     """Bytes behind a raw device pointer returned by the C ABI, as a numpy array (zero-copy view -> .cpu())."""
     class _Holder:
-        __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), True), "version": 2}
+        __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
     return torch.as_tensor(_Holder(), device=DEV).cpu().numpy().view(dtype)
 
 
@@ -136,7 +136,7 @@ def test_finalize_num_return_and_errors():
 # ------------------------------------------------------------------------------------------------
 # GEMM family vs float64 matmul
 # ------------------------------------------------------------------------------------------------
-GEMM_TOL = {"fp32": 2e-6, "tf32x3": 4e-6, "bf16x3": 6e-5, "tf32": 2e-3, "bf16": 1.5e-2}
+GEMM_TOL = {"fp32": 2e-6, "tf32x3": 1e-5, "bf16x3": 6e-5, "tf32": 2e-3, "bf16": 1.5e-2}
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32x3", "bf16x3", "tf32", "bf16"])
