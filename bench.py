@@ -255,7 +255,7 @@ def run_ours(a):
         pass
     peak = peaks.get("bf16_tflops_sustained", 1400.0)
     achieved = gf.value / (gm.value / 1e3) / 1e12 if gm.value > 0 else 0.0
-    mma_mult = 3 if a.precision in ("tf32x3", "bf16x3") else 1
+    mma_mult = 3 if a.precision in ("tf32x3", "bf16x3", "fp16x3") else 1
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": None, "kernel": f"gemm_sm100_kernel[{a.precision}]" if a.precision != "fp32" else "gemm_simt_kernel",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
@@ -269,6 +269,7 @@ def run_ours(a):
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (fp32-grade split) + f64 beam scores", "bf16x3": "bf16x3 split",
+                  "fp16x3": "fp16x3 (fp32-grade split, 11-bit planes) + f64 beam scores",
                   "tf32": "tf32", "bf16": "bf16"}[a.precision],
         "data": "synthetic",
         "config": {"workload": workload_name(a), "precision": a.precision, "global_batch": world * B,

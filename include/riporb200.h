@@ -133,7 +133,10 @@ typedef enum {
   RB200_PREC_TF32X3 = 1,  /* tcgen05 kind::tf32, error-compensated 3-MMA split: fp32-grade, parity mode */
   RB200_PREC_BF16X3 = 2,  /* tcgen05 kind::f16 (bf16), 3-MMA split: ~2^-16 relative */
   RB200_PREC_TF32 = 3,    /* single tf32 MMA */
-  RB200_PREC_BF16 = 4     /* single bf16 MMA: throughput mode, not parity-safe */
+  RB200_PREC_BF16 = 4,    /* single bf16 MMA: throughput mode, not parity-safe */
+  RB200_PREC_FP16X3 = 5   /* tcgen05 kind::f16 (fp16), 3-MMA split: tf32x3's 11-bit planes at half the bytes and
+                             twice the MMA rate. fp16 range: activations beyond +-65000 raise an overflow flag and
+                             the search returns NaN scores (use tf32x3 for such checkpoints) */
 } rb200_precision;
 
 typedef struct {

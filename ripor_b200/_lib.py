@@ -29,7 +29,7 @@ class EngineConfig(C.Structure):
                 ("max_src_len", c_i32), ("precision", c_i32), ("device", c_i32)]
 
 
-PRECISIONS = {"fp32": 0, "tf32x3": 1, "bf16x3": 2, "tf32": 3, "bf16": 4}
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "bf16x3": 2, "tf32": 3, "bf16": 4, "fp16x3": 5}
 
 # name -> (restype, argtypes); every symbol include/riporb200.h declares.
 SIGNATURES = {

@@ -84,7 +84,9 @@ struct rb200_engine {
   size_t ev_used = 0;
   double prof_flops = 0.0;
 
-  ActOut act(void* base, int64_t row_len) const { return ActOut{base, Mcap * row_len, mode}; }
+  int* overflow = nullptr;         // device flags: [0] activation overflow of the batch in flight, [1] weights
+
+  ActOut act(void* base, int64_t row_len) const { return ActOut{base, Mcap * row_len, mode, overflow}; }
 };
 
 namespace {
@@ -103,7 +105,8 @@ int alloc_packed(rb200_engine* e, Packed* w, int64_t N, int64_t K) {
 // pack `rows` x K fp32 rows into row offset `row0` of packed weight w
 int pack_rows(rb200_engine* e, Packed* w, int64_t row0, const float* src, int64_t rows, cudaStream_t s) {
   char* dst = static_cast<char*>(w->ptr) + row0 * w->K * e->elem;
-  return rb::launch_pack_planes(src, dst, rows * w->K, w->plane, e->mode, s);
+  const float scale = rb::prec_is_fp16(e->mode) ? rb::kFp16WeightScale : 1.0f;
+  return rb::launch_pack_planes(src, dst, rows * w->K, w->plane, e->mode, scale, e->overflow + 1, s);
 }
 
 int copy_f32(float* dst, const float* src, int64_t n, cudaStream_t s) {
@@ -119,6 +122,7 @@ int gemm(rb200_engine* e, const void* A, int64_t a_row_len, const Packed& w, flo
   g.W = w.ptr; g.w_plane = w.plane;
   g.C = C; g.ldc = ldc; g.act = act;
   g.M = M; g.N = w.N; g.K = w.K; g.epilogue = epi;
+  g.out_scale = rb::prec_is_fp16(e->mode) ? 1.0f / rb::kFp16WeightScale : 1.0f;
   if (!e->profiling) return rb::launch_gemm(g, s);
   // profiling pass: bracket every GEMM launch with events on its own stream (bench.py roofline leg)
   if (e->ev_used + 2 > e->events.size()) {
@@ -132,6 +136,12 @@ int gemm(rb200_engine* e, const void* A, int64_t a_row_len, const Packed& w, flo
   e->ev_used += 2;
   e->prof_flops += 2.0 * (double)M * (double)w.N * (double)w.K;
   return st;
+}
+
+// fp16x3: an activation left the fp16 range somewhere in this search -> make the result unmistakably invalid
+__global__ void poison_on_overflow_kernel(float* scores, int n, const int* flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && *flag) scores[i] = __int_as_float(0x7fc00000);
 }
 
 int build_bias_tables(rb200_engine* e, int S, cudaStream_t s) {
@@ -163,12 +173,24 @@ int build_bias_tables(rb200_engine* e, int S, cudaStream_t s) {
 
 }  // namespace
 
+static float half_bits_to_float(uint16_t h) {
+  const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ffu;
+  if (exp == 0) {
+    const float v = ldexpf((float)man, -24);
+    return sign ? -v : v;
+  }
+  const uint32_t b = sign | ((exp == 31 ? 255u : exp + 112u) << 23) | (man << 13);
+  float f;
+  memcpy(&f, &b, 4);
+  return f;
+}
+
 extern "C" {
 
 int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
   RB_REQUIRE(cfg && out, "null argument");
   RB_REQUIRE(cfg->d_kv == 64, "d_kv must be 64 (t5-base/large), got %d", cfg->d_kv);
-  RB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 4, "unknown precision %d", cfg->precision);
+  RB_REQUIRE(cfg->precision >= 0 && cfg->precision <= 5, "unknown precision %d", cfg->precision);
   RB_REQUIRE(cfg->d_model % 8 == 0 && cfg->d_ff % 8 == 0, "d_model and d_ff must be multiples of 8");
   RB_REQUIRE(cfg->decoder_vocab_size % 4 == 0, "decoder_vocab_size must be a multiple of 4");
   RB_REQUIRE(cfg->max_batch >= 1 && cfg->max_beams >= 1 && cfg->max_src_len >= 1 && cfg->docid_len >= 1,
@@ -240,6 +262,8 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
   RB_TRY(dev_alloc(e, (void**)&e->seq_dev, e->Rcap * (e->Lmodel + 1) * 8));
   RB_TRY(dev_alloc(e, (void**)&e->score_dev, e->Rcap * 4));
   RB_TRY(dev_alloc(e, (void**)&e->leaf_dev, e->Rcap * 2 * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->overflow, 2 * 4));
+  RB_CUDA(cudaMemset(e->overflow, 0, 8));
   // planes of the activation buffers may be read past M by TMA boxes: start from defined contents
   RB_CUDA(cudaMemset(e->xn, 0, (size_t)(e->Mcap * d * pe)));
   RB_CUDA(cudaMemset(e->ctx, 0, (size_t)(e->Mcap * inner * pe)));
@@ -262,7 +286,7 @@ int rb200_engine_free(rb200_engine* e) {
   for (auto p : e->in_tab) cudaFree(p);
   void* bufs[] = {e->shared_emb, e->start_emb, e->enc_final_ln, e->dec_final_ln, e->dec_bias, e->enc_bias, e->x,
                   e->xn, e->qkv, e->q2, e->ctx, e->hbuf, e->logits, e->cross_kv, e->enc_out, e->cache_k, e->cache_v,
-                  e->ids_dev, e->mask_dev, e->seq_dev, e->score_dev, e->leaf_dev};
+                  e->ids_dev, e->mask_dev, e->seq_dev, e->score_dev, e->leaf_dev, e->overflow};
   for (void* b : bufs) cudaFree(b);
   rb200_beam_free(e->beam);
   for (auto ev : e->events) cudaEventDestroy(ev);
@@ -394,6 +418,10 @@ int rb200_engine_finalize_weights(rb200_engine* e, void* stream) {
     if (!e->have.count(n)) return rb::fail(RB200_ERR_STATE, "weight %s has not been set", n.c_str());
   RB_TRY(build_bias_tables(e, 0, (cudaStream_t)stream));
   RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  int wflag = 0;
+  RB_CUDA(cudaMemcpy(&wflag, e->overflow + 1, 4, cudaMemcpyDeviceToHost));
+  if (wflag)
+    return rb::fail(RB200_ERR_INVALID, "a weight exceeds the fp16 range after the 2^8 pre-scale: use tf32x3");
   e->finalized = true;
   return 0;
 }
@@ -502,6 +530,7 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
              "`num_return_sequences` has to be smaller or equal to `num_beams`.");
   RB_REQUIRE(trie->V == e->V, "trie V=%d but the model's decoder_vocab_size is %d", trie->V, e->V);
   const int64_t launches0 = rb::launch_count();
+  RB_CUDA(cudaMemsetAsync(e->overflow, 0, 4, (cudaStream_t)stream));
   RB_TRY(rb200_engine_encode(e, ids, mask, batch, S, num_beams, stream));
   RB_TRY(rb200_beam_reset(e->beam, trie, batch, stream));
   for (int t = 0; t < max_new_tokens; ++t) {
@@ -511,6 +540,12 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
                            more ? e->in_tab[t] : nullptr, more ? e->x : nullptr, e->d, stream));
   }
   RB_TRY(rb200_beam_finalize(e->beam, trie, num_return, 1.0, sequences, scores, leaf, stream));
+  if (rb::prec_is_fp16(e->mode)) {
+    const int n = batch * num_return;
+    poison_on_overflow_kernel<<<rb::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(scores, n, e->overflow);
+    RB_CUDA(cudaGetLastError());
+    rb::launch_count()++;
+  }
   e->launches = rb::launch_count() - launches0;
   return 0;
 }
@@ -563,19 +598,21 @@ int rb200_engine_get_profile(rb200_engine* e, double* gemm_ms, double* gemm_flop
 int rb200_gemm(int precision, const float* A, const float* W, float* C, int64_t M, int64_t N, int64_t K,
                int accumulate, int relu, void* stream) {
   RB_REQUIRE(A && W && C, "null argument");
-  RB_REQUIRE(precision >= 0 && precision <= 4, "unknown precision %d", precision);
+  RB_REQUIRE(precision >= 0 && precision <= 5, "unknown precision %d", precision);
   RB_REQUIRE(!(accumulate && relu), "accumulate and relu are exclusive");
   cudaStream_t s = (cudaStream_t)stream;
   const int planes = rb::prec_planes(precision), elem = rb::prec_elem_bytes(precision);
   void *Ap = nullptr, *Wp = nullptr, *Rp = nullptr;
   RB_CUDA(cudaMalloc(&Ap, (size_t)planes * M * K * elem));
   RB_CUDA(cudaMalloc(&Wp, (size_t)planes * N * K * elem));
-  int st = rb::launch_pack_planes(A, Ap, M * K, M * K, precision, s);
-  if (st == 0) st = rb::launch_pack_planes(W, Wp, N * K, N * K, precision, s);
+  const float wscale = rb::prec_is_fp16(precision) ? rb::kFp16WeightScale : 1.0f;
+  int st = rb::launch_pack_planes(A, Ap, M * K, M * K, precision, 1.0f, nullptr, s);
+  if (st == 0) st = rb::launch_pack_planes(W, Wp, N * K, N * K, precision, wscale, nullptr, s);
   GemmArgs g;
   g.mode = precision; g.A = Ap; g.a_plane = M * K; g.W = Wp; g.w_plane = N * K;
   g.C = C; g.ldc = N; g.M = M; g.N = N; g.K = K;
   g.epilogue = accumulate ? rb::EPI_RESIDUAL : rb::EPI_STORE;
+  g.out_scale = 1.0f / wscale;
   g.act = ActOut{};
   if (relu) {   // ReLU epilogue writes planes; unpack plane 0 (+ plane 1) back to fp32 for the caller
     if (cudaMalloc(&Rp, (size_t)planes * M * N * elem) != cudaSuccess) st = RB200_ERR_CUDA;
@@ -593,9 +630,14 @@ int rb200_gemm(int precision, const float* A, const float* W, float* C, int64_t 
       for (int p = 0; p < planes; ++p) {
         if (elem == 4) v += reinterpret_cast<float*>(host.data())[p * M * N + i];
         else {
-          uint32_t b = (uint32_t)reinterpret_cast<uint16_t*>(host.data())[p * M * N + i] << 16;
+          const uint16_t h16 = reinterpret_cast<uint16_t*>(host.data())[p * M * N + i];
           float f;
-          memcpy(&f, &b, 4);
+          if (rb::prec_is_fp16(precision)) {
+            f = half_bits_to_float(h16);
+          } else {
+            const uint32_t b = (uint32_t)h16 << 16;
+            memcpy(&f, &b, 4);
+          }
           v += f;
         }
       }

@@ -15,6 +15,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <cstdlib>
+#include <cstring>
 #include <mutex>
 #include <unordered_map>
 
@@ -130,7 +132,7 @@ template <int ELEM_BYTES, int NTERMS, int BN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                   float* __restrict__ C, int64_t ldc, ActOut act, int M, int N, int K, int a_plane_rows,
-                  int w_plane_rows, int epilogue) {
+                  int w_plane_rows, int epilogue, uint32_t idesc, float out_scale) {
   using cfg = Cfg<ELEM_BYTES, NTERMS, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -185,7 +187,6 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   } else if (warp == 1) {
     // ===== MMA issuer (single elected lane) =====
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(ELEM_BYTES == 4 ? 2 : 1, BN);
       for (int kb = 0; kb < num_kb; ++kb) {
         const int s = kb % cfg::STAGES;
         const uint32_t ph = (kb / cfg::STAGES) & 1;
@@ -226,8 +227,8 @@ gemm_sm100_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         for (int j = 0; j < 32; j += 4) {
           const int n = n0 + c0 + j;
           if (n >= N) break;
-          float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                 __uint_as_float(r[j + 3]));
+          float4 v = make_float4(__uint_as_float(r[j]) * out_scale, __uint_as_float(r[j + 1]) * out_scale,
+                                 __uint_as_float(r[j + 2]) * out_scale, __uint_as_float(r[j + 3]) * out_scale);
           if (epilogue == EPI_RELU_ACT) {
             v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
             act_store4(act, (int64_t)m * N + n, v);
@@ -337,7 +338,9 @@ int launch_cfg(const GemmArgs& g, cudaStream_t s) {
   RB_TRY(get_tensor_map(g.W, w_rows, g.K, BN, ELEM_BYTES, &tmW));
   dim3 grid(ceil_div(g.N, BN), ceil_div(g.M, BM));
   kern<<<grid, kThreads, cfg::SMEM, s>>>(tmA, tmW, g.C, g.ldc, g.act, (int)g.M, (int)g.N, (int)g.K,
-                                         (int)a_plane_rows, (int)w_plane_rows, g.epilogue);
+                                         (int)a_plane_rows, (int)w_plane_rows, g.epilogue,
+                                         make_idesc(ELEM_BYTES == 4 ? 2 : (prec_is_fp16(g.mode) ? 0 : 1), BN),
+                                         g.out_scale);
   RB_CUDA(cudaGetLastError());
   rb::launch_count()++;
   return 0;
@@ -353,7 +356,20 @@ int launch_bn(const GemmArgs& g, cudaStream_t s) {
 
 }  // namespace
 
+// shared with gemm_sm100_2cta.cu
+int tensor_map_2d(const void* ptr, int64_t rows, int64_t k, int box_rows, int elem, CUtensorMap* out) {
+  return get_tensor_map(ptr, rows, k, box_rows, elem, out);
+}
+
+int launch_gemm_sm100_2cta(const GemmArgs& g, cudaStream_t s);
+
 int launch_gemm_sm100(const GemmArgs& g, cudaStream_t s) {
+  // RB200_GEMM=1cta keeps the single-CTA 128xBN kernel; default is the cta_group::2 pair kernel
+  static const bool use_pair = []() {
+    const char* e = getenv("RB200_GEMM");
+    return !(e && strcmp(e, "1cta") == 0);
+  }();
+  if (use_pair) return launch_gemm_sm100_2cta(g, s);
   const int elem = prec_elem_bytes(g.mode);
   RB_REQUIRE(g.K % (16 / elem) == 0, "K=%lld must be a multiple of %d for TMA", (long long)g.K, 16 / elem);
   RB_REQUIRE(g.N % 4 == 0, "N=%lld must be a multiple of 4", (long long)g.N);
@@ -364,6 +380,7 @@ int launch_gemm_sm100(const GemmArgs& g, cudaStream_t s) {
     case RB200_PREC_BF16X3: return launch_bn<2, 3>(g, s);
     case RB200_PREC_TF32: return launch_bn<4, 1>(g, s);
     case RB200_PREC_BF16: return launch_bn<2, 1>(g, s);
+    case RB200_PREC_FP16X3: return launch_bn<2, 3>(g, s);
     default: return fail(RB200_ERR_INVALID, "precision %d has no tensor-core GEMM", g.mode);
   }
 }

@@ -176,24 +176,76 @@ __global__ void self_attn_decode_kernel(SelfAttnArgs a, ActOut ctx) {
   }
 }
 
+// Cross-attention for the decoder step: one CTA per (query, chunk of <= NBC beams). The query's K/V rows are
+// loaded ONCE per CTA and reused for every beam of the chunk (they are identical for all beams of a query:
+// the reference expands them x num_beams, generation.py:231-233, we never do), which divides the L2 traffic
+// of this kernel by num_beams.
+constexpr int NBC = 10;
+
 __global__ void cross_attn_decode_kernel(CrossAttnArgs a, ActOut ctx) {
-  extern __shared__ float smem[];
+  extern __shared__ float smem[];   // scores [NBC][H][S]
   const int inner = a.H * 64, c4n = inner >> 2;
-  const int m = blockIdx.x, c = threadIdx.x;
+  const int b = blockIdx.x, c = threadIdx.x;
   const bool active = c < c4n;
-  const int h = c >> 4;
-  const int b = m / a.rows_per_query;
-  float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) q4 = reinterpret_cast<const float4*>(a.q + (int64_t)m * inner)[c];
-  const float* base = a.kv + (int64_t)b * a.S * a.ld;
-  const int64_t* mk = a.mask + (int64_t)b * a.S;
-  const int64_t ld = a.ld, ko = a.k_off, vo = a.v_off;
-  const float4 o = attn_core(
-      q4, h, c, active, a.H, a.S, smem,
-      [&](int p) { return reinterpret_cast<const float4*>(base + p * ld + ko); },
-      [&](int p) { return reinterpret_cast<const float4*>(base + p * ld + vo); },
-      [&](int p) { return mk[p] != 0; }, [&](int, int) { return 0.f; });
-  if (active) act_store4(ctx, (int64_t)m * inner + (int64_t)c * 4, o);
+  const int h = active ? (c >> 4) : 0;
+  const int lane16 = threadIdx.x & 15;
+  const int rpq = a.rows_per_query, S = a.S, H = a.H;
+  const int i0 = blockIdx.y * NBC;
+  const int nact = min(NBC, rpq - i0);
+  const int64_t row0 = (int64_t)b * rpq + i0;
+  float4 q4[NBC];
+#pragma unroll
+  for (int i = 0; i < NBC; ++i)
+    q4[i] = (active && i < nact) ? reinterpret_cast<const float4*>(a.q + (row0 + i) * inner)[c]
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float* base = a.kv + (int64_t)b * S * a.ld;
+  const int64_t* mk = a.mask + (int64_t)b * S;
+  const int64_t ld = a.ld;
+  for (int p = 0; p < S; ++p) {
+    const bool ok = mk[p] != 0;
+    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok && active) k4 = __ldg(reinterpret_cast<const float4*>(base + p * ld + a.k_off) + c);
+#pragma unroll
+    for (int i = 0; i < NBC; ++i) {
+      float part = q4[i].x * k4.x + q4[i].y * k4.y + q4[i].z * k4.z + q4[i].w * k4.w;
+      part += __shfl_xor_sync(0xffffffffu, part, 8);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      if (active && lane16 == 0 && i < nact) smem[(i * H + h) * S + p] = ok ? part : -INFINITY;
+    }
+  }
+  __syncthreads();
+  for (int i = 0; i < nact; ++i) {   // softmax of row (i, h) by the 16 threads of head h
+    float* sc = smem + (i * H + h) * S;
+    float m = -INFINITY;
+    for (int p = lane16; p < S; p += 16) m = fmaxf(m, sc[p]);
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o, 16));
+    float sum = 0.f;
+    for (int p = lane16; p < S; p += 16) sum += expf(sc[p] - m);
+    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, 16);
+    __syncwarp();
+    if (active)
+      for (int p = lane16; p < S; p += 16) sc[p] = expf(sc[p] - m) / sum;
+  }
+  __syncthreads();
+  float4 o4[NBC];
+#pragma unroll
+  for (int i = 0; i < NBC; ++i) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    for (int p = 0; p < S; ++p) {
+      if (mk[p] == 0) continue;
+      const float4 v4 = __ldg(reinterpret_cast<const float4*>(base + p * ld + a.v_off) + c);
+#pragma unroll
+      for (int i = 0; i < NBC; ++i) {
+        const float pr = (i < nact) ? smem[(i * H + h) * S + p] : 0.f;
+        o4[i].x += pr * v4.x; o4[i].y += pr * v4.y; o4[i].z += pr * v4.z; o4[i].w += pr * v4.w;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < NBC; ++i)
+      if (i < nact) act_store4(ctx, (row0 + i) * inner + (int64_t)c * 4, o4[i]);
+  }
 }
 
 __global__ void enc_attn_kernel(EncAttnArgs a, ActOut ctx) {
@@ -278,9 +330,9 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   }
 }
 
-__global__ void pack_planes_kernel(const float* __restrict__ src, ActOut out, int64_t numel) {
+__global__ void pack_planes_kernel(const float* __restrict__ src, ActOut out, int64_t numel, float scale) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < numel) act_store(out, i, src[i]);
+  if (i < numel) act_store(out, i, src[i] * scale);
 }
 
 }  // namespace
@@ -333,9 +385,17 @@ int launch_self_attn_decode(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s) {
 
 int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s) {
   const int threads = attn_threads(a.H);
-  const size_t smem = (size_t)a.H * a.S * sizeof(float);
-  RB_REQUIRE(smem <= 48 * 1024, "H*S=%d too large for the cross-attention kernel", a.H * a.S);
-  cross_attn_decode_kernel<<<a.M, threads, smem, s>>>(a, ctx);
+  const size_t smem = (size_t)NBC * a.H * a.S * sizeof(float);
+  RB_REQUIRE(smem <= 200 * 1024, "H*S=%d too large for the cross-attention kernel", a.H * a.S);
+  static size_t smem_attr = 48 * 1024;
+  if (smem > smem_attr) {
+    RB_CUDA(cudaFuncSetAttribute(cross_attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    smem_attr = smem;
+  }
+  RB_REQUIRE(a.M % a.rows_per_query == 0, "row count %d is not a multiple of rows_per_query %d", a.M,
+             a.rows_per_query);
+  dim3 grid(a.M / a.rows_per_query, ceil_div(a.rows_per_query, NBC));
+  cross_attn_decode_kernel<<<grid, threads, smem, s>>>(a, ctx);
   RB_CUDA(cudaGetLastError());
   rb::launch_count()++;
   return 0;
@@ -362,9 +422,10 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t s) {
   return 0;
 }
 
-int launch_pack_planes(const float* src, void* dst, int64_t numel, int64_t plane, int mode, cudaStream_t s) {
+int launch_pack_planes(const float* src, void* dst, int64_t numel, int64_t plane, int mode, float scale,
+                       int* overflow, cudaStream_t s) {
   if (numel == 0) return 0;
-  pack_planes_kernel<<<ceil_div(numel, 256), 256, 0, s>>>(src, ActOut{dst, plane, mode}, numel);
+  pack_planes_kernel<<<ceil_div(numel, 256), 256, 0, s>>>(src, ActOut{dst, plane, mode, overflow}, numel, scale);
   RB_CUDA(cudaGetLastError());
   rb::launch_count()++;
   return 0;

@@ -22,7 +22,11 @@ struct GemmArgs {
   ActOut act;            // EPI_RELU_ACT output (row length N)
   int64_t M, N, K;
   int epilogue;
+  float out_scale = 1.0f;  // accumulator multiplier (undoes the power-of-two pre-scale of fp16 weight planes)
 };
+
+// fp16 weight planes are stored multiplied by 2^8 so that the low plane stays in fp16's normal range
+constexpr float kFp16WeightScale = 256.0f;
 
 // x[row, :] = table[ids[row], :]            (encoder token embedding, shared.weight)
 int launch_embed_rows(const float* table, const int64_t* ids, float* x, int64_t rows, int d, cudaStream_t s);
@@ -70,7 +74,9 @@ inline int launch_gemm(const GemmArgs& g, cudaStream_t s) {
 }
 
 // fp32 [rows, cols] -> packed planes of `mode` (weights at load time, and rb200_gemm's operands)
-int launch_pack_planes(const float* src, void* dst, int64_t numel, int64_t plane, int mode, cudaStream_t s);
+// every element is multiplied by `scale` first; `overflow` (device int, may be null) is raised by fp16 planes
+int launch_pack_planes(const float* src, void* dst, int64_t numel, int64_t plane, int mode, float scale,
+                       int* overflow, cudaStream_t s);
 
 // HF T5 relative position bucket (host; float32 arithmetic like torch)
 int relative_bucket(int rel, bool bidirectional, int num_buckets, int max_distance);

@@ -136,10 +136,10 @@ def test_finalize_num_return_and_errors():
 # ------------------------------------------------------------------------------------------------
 # GEMM family vs float64 matmul
 # ------------------------------------------------------------------------------------------------
-GEMM_TOL = {"fp32": 2e-6, "tf32x3": 1e-5, "bf16x3": 6e-5, "tf32": 2e-3, "bf16": 1.5e-2}
+GEMM_TOL = {"fp32": 2e-6, "tf32x3": 1e-5, "fp16x3": 2e-5, "bf16x3": 6e-5, "tf32": 2e-3, "bf16": 1.5e-2}
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "bf16x3", "tf32", "bf16"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32x3", "fp16x3", "bf16x3", "tf32", "bf16"])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 256, 128), (2560, 2304, 768), (77, 16, 128), (40, 768, 3072),
                                    (300, 3072, 768), (1, 256, 768)])
 def test_gemm_modes_against_float64(mode, M, N, K):
@@ -164,7 +164,7 @@ def test_gemm_modes_against_float64(mode, M, N, K):
     Cd = torch.zeros((M, N), device=DEV)
     _lib.check(_lib.lib().rb200_gemm(_lib.PRECISIONS[mode], Ad.data_ptr(), Wd.data_ptr(), Cd.data_ptr(), M, N, K,
                                      0, 1, _sp()))
-    tol = GEMM_TOL[mode] if mode in ("fp32", "tf32x3", "bf16x3") else 1.5e-2
+    tol = GEMM_TOL[mode] if mode in ("fp32", "tf32x3", "fp16x3", "bf16x3") else 1.5e-2
     err = (Cd.cpu().double() - ref.clamp(min=0)).abs().max().item() / ref.abs().max().item()
     assert err < max(tol, 1e-5), (mode, "relu", err)
 
@@ -185,7 +185,7 @@ def _engine_search(model, trie, ids, mask, nb, L, log_softmax=False, keep=None, 
     return out
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3"])
 @pytest.mark.parametrize("name", ["tiny_plain", "tiny_logsoftmax", "tiny_shared_scaleup", "tiny_few_docs", "c1_t5base"])
 def test_search_matches_golden_from_literal_reference(name, precision):
     c, dims, w, codes, ids, mask, g = helpers.load_golden(name)
@@ -215,7 +215,7 @@ def test_search_matches_golden_from_literal_reference(name, precision):
             assert abs(run[q][k] - gold[str(q)][k]) < 1e-3 * c["L"]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "bf16x3"])
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3", "bf16x3"])
 def test_t5base_search_matches_cached_oracle(precision):
     """t5-base, 100k-doc trie, L=32, beam=10: DocIDs exact, scores within 1e-3 (north-star tolerances)."""
     L, nb, B, V = 32, 10, 6, 256
@@ -247,3 +247,23 @@ def test_fast_modes_run_and_stay_close():
         out = _engine_search(model, trie, ids, mask, nb, L, precision=precision)
         top = out.sequences_scores.view(B, nb)[:, 0].cpu()
         assert torch.allclose(top, ref_sc.view(B, nb)[:, 0], atol=tol), precision
+
+
+def test_fp16x3_overflow_is_loud():
+    """fp16x3 cannot represent |x| > 65504: the engine must return NaN scores, never silently wrong DocIDs."""
+    dims = syn.T5Dims.tiny()
+    w = syn.make_weights(dims)
+    w = dict(w)
+    w["decoder.block.0.layer.0.layer_norm.weight"] = w["decoder.block.0.layer.0.layer_norm.weight"] * 1e5
+    codes = syn.make_codes(400, dims.docid_len, dims.decoder_vocab_size)
+    ids, mask = syn.make_queries(2, S=12, vocab_size=dims.vocab_size)
+    model = T5SeqAQEncoder.from_weights(dims, w)
+    trie = DocidTrie.from_codes(codes, dims.decoder_vocab_size)
+    out = _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="fp16x3")
+    assert torch.isnan(out.sequences_scores).all()
+    out = _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="tf32x3")
+    assert not torch.isnan(out.sequences_scores).any()
+    # a weight that does not fit fp16 after the 2^8 pre-scale is refused when the engine is built
+    w["decoder.block.0.layer.2.DenseReluDense.wi.weight"] = w["decoder.block.0.layer.2.DenseReluDense.wi.weight"] * 3e4
+    with pytest.raises(ValueError, match="fp16 range"):
+        _engine_search(T5SeqAQEncoder.from_weights(dims, w), trie, ids, mask, 4, dims.docid_len, precision="fp16x3")
