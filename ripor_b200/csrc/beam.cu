@@ -54,6 +54,8 @@ __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = a.nb, V = a.tv.V, words = a.tv.words, t = a.t;
   const int total = nb * V;
+  rb::pdl_trigger();
+  rb::pdl_wait();
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* bs = reinterpret_cast<double*>(smem_raw);            // [nb]
@@ -99,7 +101,9 @@ __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
     if (a.apply_ls) x = (x - row_max[i]) - row_log[i];
     const bool ok = (allow[i * words + (v >> 5)] >> (v & 31)) & 1u;
     const double processed = ok ? (double)x : (double)x + (-1e9);   // s + (1 - mask) * (-1e9)
-    return processed + bs[i];
+    const double val = processed + bs[i];
+    // a NaN logit (e.g. after an fp16x3 range overflow) must not derail the selection: rank it last, by index
+    return val == val ? val : -1.7976931348623157e308;
   };
   uint32_t taken[kMaxPerThread / 32] = {0u, 0u, 0u, 0u};
   const int K = (total + THREADS - 1) / THREADS;
@@ -292,11 +296,10 @@ int rb200_beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits,
                       (size_t)nb * a.tv.words * sizeof(uint32_t);
   const int64_t total = (int64_t)nb * bm->V;
   if (total <= 256 * 32) {
-    beam_step_kernel<256><<<bm->batch, 256, smem, (cudaStream_t)stream>>>(a);
+    RB_CUDA(rb::launch_pdl(beam_step_kernel<256>, dim3(bm->batch), dim3(256), smem, (cudaStream_t)stream, a));
   } else {
-    beam_step_kernel<1024><<<bm->batch, 1024, smem, (cudaStream_t)stream>>>(a);
+    RB_CUDA(rb::launch_pdl(beam_step_kernel<1024>, dim3(bm->batch), dim3(1024), smem, (cudaStream_t)stream, a));
   }
-  RB_CUDA(cudaGetLastError());
   rb::launch_count()++;
   bm->cur = n;
   bm->step += 1;

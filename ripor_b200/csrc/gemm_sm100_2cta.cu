@@ -11,6 +11,11 @@
 //   leader CTA  warp 1: MMA issuer; tcgen05.commit.cta_group::2 ... multicast::cluster releases the stage in
 //                       both CTAs and finally publishes the accumulator to both epilogues
 //   both CTAs   warps 2..5: epilogue for their own 128 rows (tcgen05.ld -> registers -> fused epilogue)
+//
+// The kernel is PERSISTENT: at most one cluster per SM pair, each walking tiles cluster_id, cluster_id + n, ...
+// The shared-memory ring keeps streaming across tile boundaries and the TMEM accumulator is double-buffered
+// (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i+1 and the per-tile launch / prologue /
+// drain cost of the one-tile-per-CTA version (about 5 us on a 10-25 us tile at these shapes) is paid once.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -26,6 +31,8 @@ constexpr int BM = 128;                  // rows per CTA (256 per pair)
 constexpr int SWIZZLE_BYTES = 128;
 constexpr int kThreads = 192;
 constexpr uint32_t kSmemBudget = 227 * 1024;
+constexpr int kStgLd = 36;                               // padded row of the epilogue transpose tile (floats)
+constexpr uint32_t kStgBytes = 4 * 32 * kStgLd * 4;      // one 32 x 36 fp32 tile per epilogue warp
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -77,6 +84,15 @@ __device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
       ::"r"(smem_u32(bar)), "h"((uint16_t)3)
       : "memory");
 }
+// arrive on the barrier at the same offset in the leader CTA (rank 0) of the pair
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .b32 r;\n\t"
+      "mapa.shared::cluster.u32 r, %0, 0;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [r];\n\t}"
+      ::"r"(smem_u32(bar))
+      : "memory");
+}
 template <int KIND_TF32>
 __device__ __forceinline__ void tc_mma_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
@@ -125,31 +141,31 @@ struct Cfg2 {
   static constexpr uint32_t A_TILE = BM * SWIZZLE_BYTES;            // this CTA's 128 rows of A
   static constexpr uint32_t W_TILE = (BN / 2) * SWIZZLE_BYTES;      // this CTA's half of the W tile
   static constexpr uint32_t STAGE = PLANES * (A_TILE + W_TILE);
-  static constexpr int STAGES_RAW = (kSmemBudget - 2048) / STAGE;
+  static constexpr int STAGES_RAW = (kSmemBudget - 2048 - kStgBytes) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr uint32_t SMEM = STAGES * STAGE + 1024 + 256;
-  static constexpr int TMEM_COLS = BN < 32 ? 32 : BN;
+  static constexpr uint32_t SMEM = STAGES * STAGE + 1024 + 256 + kStgBytes;
+  static constexpr int TMEM_COLS = 2 * BN;                           // double-buffered accumulator
 };
 
 template <int ELEM_BYTES, int NTERMS, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        float* __restrict__ C, int64_t ldc, ActOut act, int M, int N, int K, int a_plane_rows,
-                       int w_plane_rows, int epilogue, uint32_t idesc, float out_scale) {
+                       int w_plane_rows, int epilogue, uint32_t idesc, float out_scale, int num_n_tiles,
+                       int num_tiles) {
   using cfg = Cfg2<ELEM_BYTES, NTERMS, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE);
   uint64_t* empty_bar = full_bar + cfg::STAGES;
-  uint64_t* tmem_full_bar = empty_bar + cfg::STAGES;
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + cfg::STAGES;    // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2], only the leader's copies are used
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int m0 = blockIdx.x * BM;                       // this CTA's rows (pair = two consecutive blockIdx.x)
-  const int n0 = blockIdx.y * BN;                       // the pair's columns
-  const int w0 = n0 + (int)rank * (BN / 2);             // this CTA's half of the W rows
+  const int cluster_id = blockIdx.x >> 1, num_clusters = gridDim.x >> 1;
   const int num_kb = (K + cfg::BK - 1) / cfg::BK;
 
   if (warp == 0 && lane == 0) {
@@ -159,7 +175,10 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], 8);      // 4 epilogue warps x 2 CTAs
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // both CTAs' warp 1, same destination offset (cute::TMEM::Allocator2Sm contract)
@@ -171,79 +190,127 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_before();
   cluster_sync_all();          // barriers of both CTAs initialised and TMEM allocated before any remote arrive
   tc_fence_after();
+  // everything above overlapped the tail of the previous kernel (PDL); operands are read only from here on
+  pdl_trigger();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_base_slot;
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % cfg::STAGES;
-        const uint32_t ph = (kb / cfg::STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        if (leader) mbar_expect_tx(&full_bar[s], 2 * cfg::STAGE);      // both CTAs' loads report here
-        uint8_t* st = smem + s * cfg::STAGE;
-        const int k0 = kb * cfg::BK;
+      int it = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
+        const int m0 = ((tile / num_n_tiles) * 2 + (int)rank) * BM;       // this CTA's 128 rows of the pair tile
+        const int w0 = (tile % num_n_tiles) * BN + (int)rank * (BN / 2);  // this CTA's half of the W rows
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % cfg::STAGES;
+          const uint32_t ph = (it / cfg::STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (leader) mbar_expect_tx(&full_bar[s], 2 * cfg::STAGE);      // both CTAs' loads report here
+          uint8_t* st = smem + s * cfg::STAGE;
+          const int k0 = kb * cfg::BK;
 #pragma unroll
-        for (int p = 0; p < cfg::PLANES; ++p)
-          tma_load_2d_2sm(&tmA, &full_bar[s], st + p * cfg::A_TILE, k0, m0 + p * a_plane_rows);
+          for (int p = 0; p < cfg::PLANES; ++p)
+            tma_load_2d_2sm(&tmA, &full_bar[s], st + p * cfg::A_TILE, k0, m0 + p * a_plane_rows);
 #pragma unroll
-        for (int p = 0; p < cfg::PLANES; ++p)
-          tma_load_2d_2sm(&tmW, &full_bar[s], st + cfg::PLANES * cfg::A_TILE + p * cfg::W_TILE, k0,
-                          w0 + p * w_plane_rows);
+          for (int p = 0; p < cfg::PLANES; ++p)
+            tma_load_2d_2sm(&tmW, &full_bar[s], st + cfg::PLANES * cfg::A_TILE + p * cfg::W_TILE, k0,
+                            w0 + p * w_plane_rows);
+        }
       }
     }
   } else if (warp == 1) {
     if (leader && lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % cfg::STAGES;
-        const uint32_t ph = (kb / cfg::STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int it = 0, lt = 0;
+      for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+        const int buf = lt & 1;
+        mbar_wait(&tmem_empty_bar[buf], ((lt >> 1) & 1) ^ 1);     // both epilogues have drained this accumulator
         tc_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * cfg::STAGE);
-        const uint32_t w_base = a_base + cfg::PLANES * cfg::A_TILE;
+        const uint32_t tmem_d = tmem_base + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const int s = it % cfg::STAGES;
+          const uint32_t ph = (it / cfg::STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * cfg::STAGE);
+          const uint32_t w_base = a_base + cfg::PLANES * cfg::A_TILE;
 #pragma unroll
-        for (int term = 0; term < NTERMS; ++term) {
-          const int ap = (NTERMS == 3 && term == 0) ? 1 : 0;
-          const int wp = (NTERMS == 3 && term == 1) ? 1 : 0;
-          const uint64_t adesc = make_smem_desc(a_base + ap * cfg::A_TILE);
-          const uint64_t wdesc = make_smem_desc(w_base + wp * cfg::W_TILE);
+          for (int term = 0; term < NTERMS; ++term) {
+            const int ap = (NTERMS == 3 && term == 0) ? 1 : 0;
+            const int wp = (NTERMS == 3 && term == 1) ? 1 : 0;
+            const uint64_t adesc = make_smem_desc(a_base + ap * cfg::A_TILE);
+            const uint64_t wdesc = make_smem_desc(w_base + wp * cfg::W_TILE);
 #pragma unroll
-          for (int k = 0; k < cfg::BK / cfg::UMMA_K; ++k)
-            tc_mma_pair<ELEM_BYTES == 4>(tmem_base, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc,
-                                         (uint32_t)((kb | term | k) != 0));
+            for (int k = 0; k < cfg::BK / cfg::UMMA_K; ++k)
+              tc_mma_pair<ELEM_BYTES == 4>(tmem_d, adesc + (uint64_t)(k * 2), wdesc + (uint64_t)(k * 2), idesc,
+                                           (uint32_t)((kb | term | k) != 0));
+          }
+          tc_commit_pair(&empty_bar[s]);
         }
-        tc_commit_pair(&empty_bar[s]);
+        tc_commit_pair(&tmem_full_bar[buf]);
       }
-      tc_commit_pair(tmem_full_bar);
     }
   } else {
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
     const int q = warp & 3;
-    const int m = m0 + q * 32 + lane;
+    float* stg = reinterpret_cast<float*>(smem + cfg::STAGES * cfg::STAGE + 256) + (warp - 2) * (32 * kStgLd);
+    int lt = 0;
+    for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
+    const int buf = lt & 1;
+    const int m0 = ((tile / num_n_tiles) * 2 + (int)rank) * BM;
+    const int n0 = (tile % num_n_tiles) * BN;
+    // Residual epilogue: the old values of C are an INPUT, so fetch them while the MMAs are still running
+    // (chunk 0 before waiting on the accumulator, chunk i+1 while chunk i is being transposed). Loads are issued
+    // before the stores of the previous chunk in program order: the compiler may not hoist them itself (aliasing).
+    auto load_residual = [&](int c0, float4 (&res)[8]) {
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        const int m = m0 + q * 32 + itr * 4 + (lane >> 3), n = n0 + c0 + (lane & 7) * 4;
+        res[itr] = (m < M && n < N) ? *reinterpret_cast<const float4*>(C + (int64_t)m * ldc + n)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    float4 res[8];
+    if (epilogue == EPI_RESIDUAL) load_residual(0, res);
+    mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
+    tc_fence_after();
+    // TMEM gives each lane one ROW (32 consecutive columns). Storing that way makes every warp store touch 32
+    // different lines; transposing the 32x32 chunk through a padded per-warp shared-memory tile lets 8 lanes
+    // write 128 contiguous bytes of one row (4 rows per instruction), which cuts the LSU wavefronts 8x.
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      if (m < M) {
+      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
 #pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int n = n0 + c0 + j;
-          if (n >= N) break;
-          float4 v = make_float4(__uint_as_float(r[j]) * out_scale, __uint_as_float(r[j + 1]) * out_scale,
-                                 __uint_as_float(r[j + 2]) * out_scale, __uint_as_float(r[j + 3]) * out_scale);
-          if (epilogue == EPI_RELU_ACT) {
-            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-            act_store4(act, (int64_t)m * N + n, v);
-          } else {
-            float4* dst = reinterpret_cast<float4*>(C + (int64_t)m * ldc + n);
-            if (epilogue == EPI_RESIDUAL) {
-              const float4 o = *dst;
-              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
-            }
-            *dst = v;
-          }
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(&stg[lane * kStgLd + j * 4]) =
+            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
+                        __uint_as_float(r[4 * j + 3]));
+      __syncwarp();
+      float4 vals[8];
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        float4 v = *reinterpret_cast<const float4*>(&stg[(itr * 4 + (lane >> 3)) * kStgLd + (lane & 7) * 4]);
+        v.x *= out_scale; v.y *= out_scale; v.z *= out_scale; v.w *= out_scale;
+        if (epilogue == EPI_RESIDUAL) { v.x += res[itr].x; v.y += res[itr].y; v.z += res[itr].z; v.w += res[itr].w; }
+        if (epilogue == EPI_RELU_ACT) {
+          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        vals[itr] = v;
+      }
+      if (epilogue == EPI_RESIDUAL && c0 + 32 < BN) load_residual(c0 + 32, res);
+#pragma unroll
+      for (int itr = 0; itr < 8; ++itr) {
+        const int m = m0 + q * 32 + itr * 4 + (lane >> 3), n = n0 + c0 + (lane & 7) * 4;
+        if (m < M && n < N) {
+          if (epilogue == EPI_RELU_ACT) act_store4(act, (int64_t)m * N + n, vals[itr]);
+          else *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n) = vals[itr];
         }
       }
+      __syncwarp();
+    }
+    // this warp is done reading the accumulator: tell the leader's MMA warp it may be overwritten
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[buf]);
     }
   }
   tc_fence_before();
@@ -273,21 +340,39 @@ int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
   CUtensorMap tmA, tmW;
   RB_TRY(tensor_map_2d(g.A, a_rows, g.K, BM, ELEM_BYTES, &tmA));
   RB_TRY(tensor_map_2d(g.W, w_rows, g.K, BN / 2, ELEM_BYTES, &tmW));
-  dim3 grid(2 * ceil_div(g.M, 2 * BM), ceil_div(g.N, BN));
+  const int num_n_tiles = ceil_div(g.N, BN);
+  const int num_tiles = ceil_div(g.M, 2 * BM) * num_n_tiles;
+  static int sm_pairs = 0;
+  if (sm_pairs == 0) {
+    int dev = 0, sms = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sm_pairs = sms / 2;
+  }
+  dim3 grid(2 * (num_tiles < sm_pairs ? num_tiles : sm_pairs));
   const int fmt = ELEM_BYTES == 4 ? 2 : (prec_is_fp16(g.mode) ? 0 : 1);
-  kern<<<grid, kThreads, cfg::SMEM, s>>>(tmA, tmW, g.C, g.ldc, g.act, (int)g.M, (int)g.N, (int)g.K,
-                                         (int)a_plane_rows, (int)w_plane_rows, g.epilogue, make_idesc_pair(fmt, BN),
-                                         g.out_scale);
-  RB_CUDA(cudaGetLastError());
+  RB_CUDA(launch_pdl(kern, grid, dim3(kThreads), cfg::SMEM, s, tmA, tmW, g.C, g.ldc, g.act, (int)g.M, (int)g.N,
+                     (int)g.K, (int)a_plane_rows, (int)w_plane_rows, g.epilogue, make_idesc_pair(fmt, BN), g.out_scale,
+                     num_n_tiles, num_tiles));
   launch_count()++;
   return 0;
 }
 
 template <int ELEM_BYTES, int NTERMS>
 int launch_bn2(const GemmArgs& g, cudaStream_t s) {
-  // 256x256 pair tiles when they still occupy most SMs, else 256x128
-  const int64_t ctas256 = 2 * (int64_t)ceil_div(g.M, 2 * BM) * ceil_div(g.N, 256);
-  if (g.N >= 256 && ctas256 >= 100) return launch_cfg2<ELEM_BYTES, NTERMS, 256>(g, s);
+  // Persistent schedule: every SM pair walks ceil(tiles / pairs) tiles whose duration grows with BN. Pick the
+  // tile width with the smaller (rounds x BN); ties go to 256 (fewer operand bytes per output).
+  static int sm_pairs = 0;
+  if (sm_pairs == 0) {
+    int dev = 0, sms = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    sm_pairs = sms / 2;
+  }
+  const int64_t m_pairs = ceil_div(g.M, 2 * BM);
+  const int64_t cost256 = (int64_t)ceil_div(m_pairs * ceil_div(g.N, 256), sm_pairs) * 256;
+  const int64_t cost128 = (int64_t)ceil_div(m_pairs * ceil_div(g.N, 128), sm_pairs) * 128;
+  if (g.N >= 256 && cost256 <= cost128) return launch_cfg2<ELEM_BYTES, NTERMS, 256>(g, s);
   return launch_cfg2<ELEM_BYTES, NTERMS, 128>(g, s);
 }
 

@@ -37,6 +37,8 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
                                float* __restrict__ out_f32, int64_t rows, int d, float eps, float scale) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
+  pdl_trigger();
+  pdl_wait();
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * d);
   const float4* wr = reinterpret_cast<const float4*>(w);
@@ -117,6 +119,8 @@ __global__ void self_attn_decode_kernel(SelfAttnArgs a, ActOut ctx) {
   int* anc_s = reinterpret_cast<int*>(smem);          // [L]
   float* sc = smem + a.L;                              // [H, P]
   const int arow = (a.rpq == 1) ? m * a.nb : m;
+  pdl_trigger();
+  pdl_wait();
   for (int p = threadIdx.x; p < P; p += blockDim.x) anc_s[p] = a.anc[(int64_t)arow * a.L + p];
   float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (active) {
@@ -176,75 +180,132 @@ __global__ void self_attn_decode_kernel(SelfAttnArgs a, ActOut ctx) {
   }
 }
 
-// Cross-attention for the decoder step: one CTA per (query, chunk of <= NBC beams). The query's K/V rows are
-// loaded ONCE per CTA and reused for every beam of the chunk (they are identical for all beams of a query:
-// the reference expands them x num_beams, generation.py:231-233, we never do), which divides the L2 traffic
-// of this kernel by num_beams.
-constexpr int NBC = 10;
+// Cross-attention for the decoder step. One CTA per (query, chunk of <= NBC beams, group of HG heads); warp = head.
+// The query's K/V rows are identical for all of its beams (the reference expands them x num_beams,
+// generation.py:231-233, we never do): a 32-position K (then V) chunk is staged ONCE in shared memory and
+// reused by every beam of the chunk. Phase 1: lane = key position, a full 64-dim dot product per (beam, position)
+// from shared memory (no shuffle reductions: the first version of this kernel spent its time issuing 4
+// shuffles + adds per 4-element partial dot). Phase 2: lane = a pair of output dims.
+constexpr int NBC = 10;          // beams per CTA
+constexpr int XHG = 4;           // heads per CTA
+constexpr int XLD = XHG * 64 + 4;  // padded row of the staged K/V chunk (floats): conflict-free 128-bit rows
 
-__global__ void cross_attn_decode_kernel(CrossAttnArgs a, ActOut ctx) {
-  extern __shared__ float smem[];   // scores [NBC][H][S]
-  const int inner = a.H * 64, c4n = inner >> 2;
-  const int b = blockIdx.x, c = threadIdx.x;
-  const bool active = c < c4n;
-  const int h = active ? (c >> 4) : 0;
-  const int lane16 = threadIdx.x & 15;
-  const int rpq = a.rows_per_query, S = a.S, H = a.H;
+__global__ void __launch_bounds__(XHG * 32) cross_attn_decode_kernel(CrossAttnArgs a, ActOut ctx) {
+  extern __shared__ __align__(16) float smem[];
+  const int inner = a.H * 64;
+  const int b = blockIdx.x, hg0 = blockIdx.z * XHG;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = hg0 + warp;                      // this warp's head
+  const bool head_ok = h < a.H;
+  const int rpq = a.rows_per_query, S = a.S;
   const int i0 = blockIdx.y * NBC;
   const int nact = min(NBC, rpq - i0);
   const int64_t row0 = (int64_t)b * rpq + i0;
-  float4 q4[NBC];
-#pragma unroll
-  for (int i = 0; i < NBC; ++i)
-    q4[i] = (active && i < nact) ? reinterpret_cast<const float4*>(a.q + (row0 + i) * inner)[c]
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
-  const float* base = a.kv + (int64_t)b * S * a.ld;
+  float* k_s = smem;                             // [32][XLD] staged K chunk
+  float* v_s = k_s + 32 * XLD;                   // [32][XLD] staged V chunk (prefetched while phase 1 runs)
+  float* q_s = v_s + 32 * XLD;                   // [NBC][XHG*64]
+  float* sc_s = q_s + NBC * XHG * 64;            // [NBC][XHG][S]
+  pdl_trigger();
+  pdl_wait();
+  const int cols = min(XHG, a.H - hg0) * 64;     // valid floats per staged row
+  for (int e = threadIdx.x; e < NBC * XHG * 16; e += blockDim.x) {
+    const int i = e / (XHG * 16), c4 = e - i * (XHG * 16);
+    const bool ok = i < nact && c4 * 4 < cols;
+    const float* src = a.q + (row0 + (ok ? i : 0)) * inner + hg0 * 64 + (ok ? c4 * 4 : 0);
+    const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(q_s + i * XHG * 64 + c4 * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d32), "l"(src), "r"(ok ? 16 : 0) : "memory");
+  }   // joins the commit group of the first K chunk below
+  const float* base = a.kv + (int64_t)b * S * a.ld + hg0 * 64;
   const int64_t* mk = a.mask + (int64_t)b * S;
-  const int64_t ld = a.ld;
-  for (int p = 0; p < S; ++p) {
-    const bool ok = mk[p] != 0;
-    float4 k4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ok && active) k4 = __ldg(reinterpret_cast<const float4*>(base + p * ld + a.k_off) + c);
-#pragma unroll
-    for (int i = 0; i < NBC; ++i) {
-      float part = q4[i].x * k4.x + q4[i].y * k4.y + q4[i].z * k4.z + q4[i].w * k4.w;
-      part += __shfl_xor_sync(0xffffffffu, part, 8);
-      part += __shfl_xor_sync(0xffffffffu, part, 4);
-      part += __shfl_xor_sync(0xffffffffu, part, 2);
-      part += __shfl_xor_sync(0xffffffffu, part, 1);
-      if (active && lane16 == 0 && i < nact) smem[(i * H + h) * S + p] = ok ? part : -INFINITY;
+  // 32 positions x cols floats with cp.async (16 B, zero-filled for masked / out-of-range rows): the loads of a
+  // chunk are all in flight at once instead of one L2 round trip per loop iteration
+  auto stage = [&](float* dst, int p0, int64_t off) {
+    for (int e = threadIdx.x; e < 32 * XHG * 16; e += blockDim.x) {
+      const int r = e / (XHG * 16), c4 = e - r * (XHG * 16);
+      const int p = p0 + r;
+      const bool ok = p < S && c4 * 4 < cols && mk[p < S ? p : 0] != 0;
+      const float* src = base + (int64_t)(ok ? p : 0) * a.ld + off + (ok ? c4 * 4 : 0);
+      const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst + r * XLD + c4 * 4);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d32), "l"(src), "r"(ok ? 16 : 0) : "memory");
     }
-  }
-  __syncthreads();
-  for (int i = 0; i < nact; ++i) {   // softmax of row (i, h) by the 16 threads of head h
-    float* sc = smem + (i * H + h) * S;
-    float m = -INFINITY;
-    for (int p = lane16; p < S; p += 16) m = fmaxf(m, sc[p]);
-    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o, 16));
-    float sum = 0.f;
-    for (int p = lane16; p < S; p += 16) sum += expf(sc[p] - m);
-    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, 16);
-    __syncwarp();
-    if (active)
-      for (int p = lane16; p < S; p += 16) sc[p] = expf(sc[p] - m) / sum;
-  }
-  __syncthreads();
-  float4 o4[NBC];
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  // ---- phase 1: scores[i][head][p] = q_i . k_p -------------------------------------------------------
+  stage(k_s, 0, a.k_off);
+  stage(v_s, 0, a.v_off);                        // V chunk 0 arrives while phase 1 computes
+  for (int p0 = 0; p0 < S; p0 += 32) {
+    if (p0 > 0) {
+      __syncthreads();
+      stage(k_s, p0, a.k_off);
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    }
+    __syncthreads();
+    float acc[NBC];
 #pragma unroll
-  for (int i = 0; i < NBC; ++i) o4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) {
-    for (int p = 0; p < S; ++p) {
-      if (mk[p] == 0) continue;
-      const float4 v4 = __ldg(reinterpret_cast<const float4*>(base + p * ld + a.v_off) + c);
+    for (int i = 0; i < NBC; ++i) acc[i] = 0.f;
+    const float* krow = k_s + lane * XLD + warp * 64;
+    const float* qh = q_s + warp * 64;
+#pragma unroll 4
+    for (int d4 = 0; d4 < 16; ++d4) {
+      const float4 k4 = *reinterpret_cast<const float4*>(krow + d4 * 4);
 #pragma unroll
       for (int i = 0; i < NBC; ++i) {
-        const float pr = (i < nact) ? smem[(i * H + h) * S + p] : 0.f;
-        o4[i].x += pr * v4.x; o4[i].y += pr * v4.y; o4[i].z += pr * v4.z; o4[i].w += pr * v4.w;
+        const float4 q4 = *reinterpret_cast<const float4*>(qh + i * XHG * 64 + d4 * 4);
+        acc[i] += q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
       }
     }
+    const int p = p0 + lane;
+    if (p < S) {
+      const bool ok = mk[p] != 0;
+#pragma unroll
+      for (int i = 0; i < NBC; ++i)
+        if (i < nact) sc_s[(i * XHG + warp) * S + p] = ok ? acc[i] : -INFINITY;
+    }
+  }
+  __syncthreads();
+  // ---- softmax over the S positions of every (beam, head) row: one warp per head -----------------------
+  for (int i = 0; i < nact; ++i) {
+    float* sc = sc_s + (i * XHG + warp) * S;
+    float m = -INFINITY;
+    for (int p = lane; p < S; p += 32) m = fmaxf(m, sc[p]);
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    float sum = 0.f;
+    for (int p = lane; p < S; p += 32) sum += expf(sc[p] - m);
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    for (int p = lane; p < S; p += 32) sc[p] = expf(sc[p] - m) / sum;
+  }
+  // ---- phase 2: out[i][head][2*lane .. +1] = sum_p prob[i][p] * v_p ------------------------------------
+  float2 o2[NBC];
+#pragma unroll
+  for (int i = 0; i < NBC; ++i) o2[i] = make_float2(0.f, 0.f);
+  for (int p0 = 0; p0 < S; p0 += 32) {
+    if (p0 > 0) {
+      __syncthreads();
+      stage(v_s, p0, a.v_off);
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();
+    const int np = min(32, S - p0);
+    for (int r = 0; r < np; ++r) {
+      const float2 v2 = *reinterpret_cast<const float2*>(v_s + r * XLD + warp * 64 + lane * 2);
+#pragma unroll
+      for (int i = 0; i < NBC; ++i) {
+        const float pr = (i < nact) ? sc_s[(i * XHG + warp) * S + p0 + r] : 0.f;   // masked keys: exactly 0
+        o2[i].x += pr * v2.x;
+        o2[i].y += pr * v2.y;
+      }
+    }
+  }
+  if (head_ok) {
 #pragma unroll
     for (int i = 0; i < NBC; ++i)
-      if (i < nact) act_store4(ctx, (row0 + i) * inner + (int64_t)c * 4, o4[i]);
+      if (i < nact) {
+        const int64_t idx = (row0 + i) * inner + h * 64 + lane * 2;
+        act_store(ctx, idx, o2[i].x);
+        act_store(ctx, idx + 1, o2[i].y);
+      }
   }
 }
 
@@ -357,8 +418,8 @@ int launch_broadcast_row(const float* vec, float* x, int64_t rows, int d, cudaSt
 int launch_rmsnorm(const float* x, const float* w, ActOut out, int64_t rows, int d, float eps, float scale,
                    cudaStream_t s) {
   if (rows == 0) return 0;
-  rmsnorm_kernel<false><<<ceil_div(rows, 4), 128, 0, s>>>(x, w, out, nullptr, rows, d, eps, scale);
-  RB_CUDA(cudaGetLastError());
+  RB_CUDA(launch_pdl(rmsnorm_kernel<false>, dim3(ceil_div(rows, 4)), dim3(128), 0, s, x, w, out, nullptr, rows, d, eps,
+                     scale));
   rb::launch_count()++;
   return 0;
 }
@@ -377,16 +438,15 @@ int launch_self_attn_decode(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s) {
   const int threads = attn_threads(a.H);
   RB_REQUIRE(threads <= 1024, "too many heads (%d)", a.H);
   const size_t smem = (size_t)(a.L + a.H * (a.t + 1)) * sizeof(float);
-  self_attn_decode_kernel<<<a.M, threads, smem, s>>>(a, ctx);
-  RB_CUDA(cudaGetLastError());
+  RB_CUDA(launch_pdl(self_attn_decode_kernel, dim3(a.M), dim3(threads), smem, s, a, ctx));
   rb::launch_count()++;
   return 0;
 }
 
 int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s) {
-  const int threads = attn_threads(a.H);
-  const size_t smem = (size_t)NBC * a.H * a.S * sizeof(float);
-  RB_REQUIRE(smem <= 200 * 1024, "H*S=%d too large for the cross-attention kernel", a.H * a.S);
+  const int threads = XHG * 32;
+  const size_t smem = (size_t)(2 * 32 * XLD + NBC * XHG * 64 + NBC * XHG * a.S) * sizeof(float);
+  RB_REQUIRE(smem <= 200 * 1024, "S=%d too large for the cross-attention kernel", a.S);
   static size_t smem_attr = 48 * 1024;
   if (smem > smem_attr) {
     RB_CUDA(cudaFuncSetAttribute(cross_attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -394,9 +454,8 @@ int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s)
   }
   RB_REQUIRE(a.M % a.rows_per_query == 0, "row count %d is not a multiple of rows_per_query %d", a.M,
              a.rows_per_query);
-  dim3 grid(a.M / a.rows_per_query, ceil_div(a.rows_per_query, NBC));
-  cross_attn_decode_kernel<<<grid, threads, smem, s>>>(a, ctx);
-  RB_CUDA(cudaGetLastError());
+  dim3 grid(a.M / a.rows_per_query, ceil_div(a.rows_per_query, NBC), ceil_div(a.H, XHG));
+  RB_CUDA(launch_pdl(cross_attn_decode_kernel, grid, dim3(threads), smem, s, a, ctx));
   rb::launch_count()++;
   return 0;
 }

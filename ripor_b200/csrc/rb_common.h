@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -53,5 +54,39 @@ inline int64_t& launch_count() {
   static thread_local int64_t n = 0;
   return n;
 }
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// Every hot kernel of the engine starts with pdl_trigger() + pdl_wait(): the next kernel of the stream is
+// allowed to be scheduled (and to run its prologue: barrier init, TMEM allocation, descriptor prefetch) while
+// this one is still running, and nobody touches global memory before the previous kernel has fully completed
+// and flushed. That hides the ~2-3 us launch/scheduling gap paid ~4400 times per search.
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+inline bool pdl_enabled() {
+  static const bool on = []() {
+    const char* e = getenv("RB200_PDL");     // opt-in: measured gain on B200 was ~1 % (profiles/r01_summary.md)
+    return e && e[0] == '1';
+  }();
+  return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
 
 }  // namespace rb

@@ -328,6 +328,120 @@ def evaluate_runs(args, q_paths):
                 json.dump(perf, f)
 
 
+def constrained_decode_smtid(model, dataloader, prefix_constrain_processor, smtid_to_docids, max_new_token, device,
+                             out_dir, local_rank, topk=100, apply_log_softmax_for_scores=False, write=True):
+    """reference evaluate.py:134-178: {qid: {smtid_prefix: {docid: score}}}; prefixes that are not in the trie keep
+    an empty dict. ``smtid_to_docids`` may be None: the docids of a prefix are then read from the trie leaves."""
+    qid_to_rankdata: Dict[int, Dict[str, Dict[str, float]]] = {}
+    trie: DocidTrie = prefix_constrain_processor.trie
+    for batch in dataloader:
+        outputs = generate_for_constrained_prefix_beam_search(
+            model, prefix_constrain_processor, input_ids=batch["input_ids"].long(),
+            attention_mask=batch["attention_mask"].long(), max_new_tokens=max_new_token, output_scores=True,
+            return_dict=True, return_dict_in_generate=True, num_beams=topk, num_return_sequences=topk,
+            apply_log_softmax_for_scores=apply_log_softmax_for_scores)
+        batch_qids = batch["id"].cpu().tolist()
+        str_smtids = convert_ptsmtids_to_strsmtid(outputs.sequences.view(-1, topk, max_new_token + 1), max_new_token)
+        relevant_scores = outputs.sequences_scores.view(-1, topk).cpu().tolist()
+        leaf = outputs.leaf_ranges.view(-1, topk, 2).cpu().tolist()
+        for qid, ranked_smtids, rel_scores, ranges in zip(batch_qids, str_smtids, relevant_scores, leaf):
+            qid_to_rankdata[qid] = {}
+            for smtid, rel_score, (lo, hi) in zip(ranked_smtids, rel_scores, ranges):
+                qid_to_rankdata[qid][smtid] = {}
+                if smtid_to_docids is not None:
+                    docids = smtid_to_docids.get(smtid, [])
+                else:
+                    docids = trie.docids_for_range(lo, hi)
+                for docid in docids:
+                    qid_to_rankdata[qid][smtid][docid] = rel_score if apply_log_softmax_for_scores \
+                        else rel_score * max_new_token
+    if write:
+        with open(os.path.join(out_dir, f"qid_smtid_rankdata_{local_rank}.json"), "w") as fout:
+            json.dump(qid_to_rankdata, fout)
+    return qid_to_rankdata
+
+
+def t5seq_aq_get_qid_to_smtid_rankdata(args, tokenizer=None):
+    """reference evaluate.py:528-611: beam search to DocID *prefixes* of length max_new_token in {4,8,16,32} over
+    the full-length trie, for the train queries."""
+    ddp_setup()
+    model = T5SeqAQEncoder.from_pretrained(args.pretrained_path)
+    model.eval()
+    with open(args.docid_to_smtid_path) as fin:
+        docid_to_smtids = json.load(fin)
+    V = model.config.decoder_vocab_sizes
+    if len(set(V)) == 2:
+        raise NotImplementedError
+    if len(set(V)) != 1:
+        raise ValueError("not valid decoder_vocab_size")
+    docids = list(docid_to_smtids.keys())
+    trie = DocidTrie.from_docid_to_smtid(docid_to_smtids, V[0])
+    if args.local_rank <= 0:
+        for i, n in enumerate(trie.level_counts()):
+            print(f"{i}-th step has {n:,} effective smtid ")
+    prefix_constrain_processor = PrefixConstrainLogitProcessorFastSparse.from_trie(trie)
+    assert args.max_new_token in [4, 8, 16, 32], args.max_new_token
+    assert docid_to_smtids[docids[0]][0] == -1
+    if args.local_rank <= 0:
+        os.makedirs(args.out_dir, exist_ok=True)
+    world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
+    rank = torch.distributed.get_rank() if torch.distributed.is_initialized() else 0
+    local_rank = max(args.local_rank, 0)
+    dev_dataset = CollectionDatasetWithDocIDPreLoad(data_dir=args.train_query_dir, id_style="row_id",
+                                                    tid_to_smtid_path=None, add_prefix=True, is_query=True)
+    dev_loader = CollectionDataWithDocIDLoader(dataset=dev_dataset, tokenizer_type=args.pretrained_path, max_length=256,
+                                               batch_size=args.batch_size,
+                                               sampler=distributed_sampler_indices(len(dev_dataset), world, rank),
+                                               tokenizer=tokenizer)
+    model.to(local_rank)
+    print("out_dir: ", args.out_dir)
+    model.base_model.config.decoding = True
+    return constrained_decode_smtid(model.base_model, dev_loader, prefix_constrain_processor, None, args.max_new_token,
+                                    device=local_rank, out_dir=args.out_dir, local_rank=local_rank, topk=args.topk,
+                                    apply_log_softmax_for_scores=args.apply_log_softmax_for_scores)
+
+
+def merge_rank_smtid_rankdata(subs: List[Dict]) -> Dict:
+    """reference evaluate.py:625-637."""
+    merged: Dict = {}
+    for sub in subs:
+        for qid in sub:
+            if qid not in merged:
+                merged[qid] = sub[qid]
+            else:
+                for smtid in sub[qid]:
+                    if smtid not in merged[qid]:
+                        merged[qid][smtid] = sub[qid][smtid]
+                    else:
+                        for docid, score in sub[qid][smtid].items():
+                            merged[qid][smtid][docid] = score
+    return merged
+
+
+def t5seq_aq_get_qid_to_smtid_rankdata_2(args):
+    out_dir = args.out_dir
+    if os.path.exists(os.path.join(out_dir, "qid_smtid_rankdata.json")):
+        print("old run.json exisit.")
+        os.remove(os.path.join(out_dir, "qid_smtid_rankdata.json"))
+    sub_paths = [p for p in os.listdir(out_dir) if "qid_smtid_rankdata" in p]
+    expected = args.num_ranks if args.num_ranks else torch.cuda.device_count()
+    assert len(sub_paths) == expected, (sub_paths, expected)
+    subs = []
+    for sub_path in sub_paths:
+        with open(os.path.join(out_dir, sub_path)) as fin:
+            subs.append(json.load(fin))
+    merged = merge_rank_smtid_rankdata(subs)
+    smtid_lengths = [len(v) for v in merged.values()]
+    doc_lengths = [len(d) for v in merged.values() for d in v.values()]
+    q = [0.0, 0.1, 0.25, 0.5, 0.75, 0.9, 1.0]
+    print("smtid_length per query: ", np.quantile(smtid_lengths, q))
+    print("doc_length per smtid: ", np.quantile(doc_lengths, q))
+    with open(os.path.join(out_dir, "qid_smtid_rankdata.json"), "w") as fout:
+        json.dump(merged, fout)
+    for sub_path in sub_paths:
+        os.remove(os.path.join(out_dir, sub_path))
+
+
 def get_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--task", type=str, default="")
@@ -340,6 +454,7 @@ def get_args(argv=None):
     ap.add_argument("--topk", type=int, default=200)
     ap.add_argument("--max_new_token_for_docid", type=int, default=32)
     ap.add_argument("--max_new_token", type=int, default=None)
+    ap.add_argument("--train_query_dir", type=str, default=None)
     ap.add_argument("--apply_log_softmax_for_scores", action="store_true")
     ap.add_argument("--local_rank", type=int, default=int(os.environ.get("LOCAL_RANK", -1)))
     ap.add_argument("--num_ranks", type=int, default=0, help="run_*.json files expected by the merge task "
@@ -353,9 +468,13 @@ def main(argv=None):
         t5seq_aq_retrieve_docids(args)
     elif args.task == "t5seq_aq_retrieve_docids_2":
         t5seq_aq_retrieve_docids_2(args)
+    elif args.task == "t5seq_aq_get_qid_to_smtid_rankdata":
+        t5seq_aq_get_qid_to_smtid_rankdata(args)
+    elif args.task == "t5seq_aq_get_qid_to_smtid_rankdata_2":
+        t5seq_aq_get_qid_to_smtid_rankdata_2(args)
     else:
         raise ValueError(f"task {args.task!r} is not part of the retrieval path served here "
-                         "(t5seq_aq_retrieve_docids, t5seq_aq_retrieve_docids_2)")
+                         "(t5seq_aq_retrieve_docids[_2], t5seq_aq_get_qid_to_smtid_rankdata[_2])")
 
 
 if __name__ == "__main__":
