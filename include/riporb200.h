@@ -206,6 +206,12 @@ int rb200_engine_get_profile(rb200_engine* eng, double* gemm_ms, double* gemm_fl
 int rb200_gemm(int precision, const float* A_dev, const float* W_dev, float* C_dev, int64_t M, int64_t N,
                int64_t K, int accumulate, int relu, void* stream);
 
+/* Roofline microbench of one GEMM shape: `iters` back-to-back launches (epilogue 0 store, 1 residual, 2 relu->planes)
+ * over operands rotated through `rotate_mb` MiB of copies (so weights do not stay in L2 between launches, as in a
+ * real decoder step), timed with CUDA events on `stream`. avg_us = mean device time per launch. */
+int rb200_gemm_bench(int precision, int64_t M, int64_t N, int64_t K, int epilogue, int iters, int rotate_mb,
+                     double* avg_us, void* stream);
+
 /* HF T5Attention._relative_position_bucket for one relative position (key - query), in the float32
  * arithmetic torch uses; the engine builds its bias tables with it (exposed for parity tests). */
 int rb200_relative_position_bucket(int relative_position, int bidirectional, int num_buckets, int max_distance);

@@ -84,6 +84,44 @@ __device__ __forceinline__ void act_store(const ActOut& o, int64_t idx, float v)
   }
 }
 
+// two consecutive elements, idx % 2 == 0
+__device__ __forceinline__ void act_store2(const ActOut& o, int64_t idx, float2 v) {
+  switch (o.mode) {
+    case 0:
+      *reinterpret_cast<float2*>(static_cast<float*>(o.base) + idx) = v;
+      break;
+    case 1: {
+      const float2 hi = make_float2(round_tf32(v.x), round_tf32(v.y));
+      *reinterpret_cast<float2*>(static_cast<float*>(o.base) + idx) = hi;
+      *reinterpret_cast<float2*>(static_cast<float*>(o.base) + o.plane + idx) =
+          make_float2(round_tf32(v.x - hi.x), round_tf32(v.y - hi.y));
+      break;
+    }
+    case 3:
+      *reinterpret_cast<float2*>(static_cast<float*>(o.base) + idx) = make_float2(round_tf32(v.x), round_tf32(v.y));
+      break;
+    case 5: {
+      if (!(fabsf(v.x) <= kFp16Limit && fabsf(v.y) <= kFp16Limit) && o.overflow) *o.overflow = 1;
+      __half* b = static_cast<__half*>(o.base);
+      const __half2 hi = __floats2half2_rn(v.x, v.y);
+      const float2 hf = __half22float2(hi);
+      *reinterpret_cast<__half2*>(b + idx) = hi;
+      *reinterpret_cast<__half2*>(b + o.plane + idx) = __floats2half2_rn(v.x - hf.x, v.y - hf.y);
+      break;
+    }
+    default: {   // bf16 planes
+      __nv_bfloat16* b = static_cast<__nv_bfloat16*>(o.base);
+      const __nv_bfloat162 hi = __floats2bfloat162_rn(v.x, v.y);
+      *reinterpret_cast<__nv_bfloat162*>(b + idx) = hi;
+      if (o.mode == 2) {
+        const float2 hf = __bfloat1622float2(hi);
+        *reinterpret_cast<__nv_bfloat162*>(b + o.plane + idx) = __floats2bfloat162_rn(v.x - hf.x, v.y - hf.y);
+      }
+      break;
+    }
+  }
+}
+
 // four consecutive elements, idx % 4 == 0 (vector stores)
 __device__ __forceinline__ void act_store4(const ActOut& o, int64_t idx, float4 v) {
   switch (o.mode) {

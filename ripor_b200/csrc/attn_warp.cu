@@ -1,0 +1,292 @@
+// Decode-step attention, one WARP per (decoder row, head) with lane = key position.
+//
+// Same arithmetic as the row-per-CTA kernels in kernels.cu (HF T5 attention as the reference drives it through
+// t5_pretrainer/modeling/t5_generative_retriever.py:403-416: no 1/sqrt(dk) scaling, additive relative position
+// bias in self-attention only, hard masks, fp32 softmax; the softmax is evaluated chunk by chunk of 32 keys with
+// a running maximum). What changes is the shape of the memory traffic. The first versions walked the key
+// positions in a serial loop (one dependent L2/HBM round trip per position, ~20 us per CTA); a lane-per-row
+// layout is no better (every 128-bit load touches 32 different lines: 512 L1 wavefronts per warp). Here every
+// K/V row segment (64 floats = 256 B) is read by 16 lanes as one coalesced 256 B request, all requests of a
+// chunk are in flight at once, and
+//   self   reduces q.k over the 16 lanes with shuffles (one q per K row), reads (t+1) * 2 * 256 B per (row, head)
+//          from the KV cache through the beam ancestry table: HBM-bound
+//   cross  stages the chunk in shared memory with cp.async (zero-filled for masked keys) because each K/V row is
+//          reused by all beams of the query (the reference expands the encoder states x num_beams,
+//          generation.py:231-233; we never do): n_valid * 2 * 256 B per (query, head)
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "kernels.h"
+
+namespace rb {
+namespace {
+
+constexpr int kWarps = 4;          // warps per CTA
+constexpr int kXB = 10;            // beams per warp in cross-attention
+
+__device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
+  acc = fmaf(a.x, b.x, acc);
+  acc = fmaf(a.y, b.y, acc);
+  acc = fmaf(a.z, b.z, acc);
+  return fmaf(a.w, b.w, acc);
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// self-attention against the KV cache
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kWarps * 32, 5) self_attn_warp_kernel(SelfAttnArgs a, ActOut ctx) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int wid = blockIdx.x * kWarps + warp;
+  const int m = wid / a.H, h = wid - m * a.H;
+  pdl_wait();
+  if (m >= a.M) return;
+  const int inner = a.H * 64, t = a.t, L = a.L;
+  const int arow = (a.rpq == 1) ? m * a.nb : m;
+  const float* qrow = a.qkv + (int64_t)m * 3 * inner + h * 64;
+  {
+    const int64_t dst = ((int64_t)t * a.row_cap + m) * inner + h * 64 + lane * 2;
+    *reinterpret_cast<float2*>(a.cache_k + dst) = *reinterpret_cast<const float2*>(qrow + inner + lane * 2);
+    *reinterpret_cast<float2*>(a.cache_v + dst) = *reinterpret_cast<const float2*>(qrow + 2 * inner + lane * 2);
+  }
+  const float4 q4 = *reinterpret_cast<const float4*>(qrow + l16 * 4);
+  const int64_t hoff = h * 64 + l16 * 4;
+  float run_max = -INFINITY, run_sum = 0.f;
+  float4 o4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int c0 = 0; c0 <= t; c0 += 16) {
+    const int pl = c0 + l16;
+    const int slot_l = pl < t ? pl * (int)a.row_cap + a.anc[(int64_t)arow * L + pl] : -1;
+    const float bias_l = pl <= t ? __ldg(a.bias + h * L + (t - pl)) : 0.f;
+    float4 k4[8], v4[8];
+    float bias[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int slot = __shfl_sync(0xffffffffu, slot_l, 2 * j + half);
+      bias[j] = __shfl_sync(0xffffffffu, bias_l, 2 * j + half);
+      k4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+      v4[j] = k4[j];
+      if (c0 + 2 * j + half <= t) {
+        const float* kp = slot >= 0 ? a.cache_k + (int64_t)slot * inner + hoff : qrow + inner + l16 * 4;
+        const float* vp = slot >= 0 ? a.cache_v + (int64_t)slot * inner + hoff : qrow + 2 * inner + l16 * 4;
+        k4[j] = *reinterpret_cast<const float4*>(kp);
+        v4[j] = *reinterpret_cast<const float4*>(vp);
+      }
+    }
+    float sc[8];
+    float cmax = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float part = dot4(q4, k4[j], 0.f);
+      part += __shfl_xor_sync(0xffffffffu, part, 8);
+      part += __shfl_xor_sync(0xffffffffu, part, 4);
+      part += __shfl_xor_sync(0xffffffffu, part, 2);
+      part += __shfl_xor_sync(0xffffffffu, part, 1);
+      sc[j] = (c0 + 2 * j + half <= t) ? part + bias[j] : -INFINITY;
+      cmax = fmaxf(cmax, sc[j]);
+    }
+    cmax = fmaxf(cmax, __shfl_xor_sync(0xffffffffu, cmax, 16));
+    const float new_max = fmaxf(run_max, cmax);
+    const float rescale = expf(run_max - new_max);
+    run_max = new_max;
+    o4.x *= rescale; o4.y *= rescale; o4.z *= rescale; o4.w *= rescale;
+    float csum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float e = expf(sc[j] - new_max);
+      csum += e;
+      o4.x = fmaf(e, v4[j].x, o4.x); o4.y = fmaf(e, v4[j].y, o4.y);
+      o4.z = fmaf(e, v4[j].z, o4.z); o4.w = fmaf(e, v4[j].w, o4.w);
+    }
+    run_sum = run_sum * rescale + csum + __shfl_xor_sync(0xffffffffu, csum, 16);
+  }
+  pdl_trigger();
+  o4.x += __shfl_xor_sync(0xffffffffu, o4.x, 16);
+  o4.y += __shfl_xor_sync(0xffffffffu, o4.y, 16);
+  o4.z += __shfl_xor_sync(0xffffffffu, o4.z, 16);
+  o4.w += __shfl_xor_sync(0xffffffffu, o4.w, 16);
+  if (half == 0) {
+    const float inv = 1.0f / run_sum;
+    act_store4(ctx, (int64_t)m * inner + hoff, make_float4(o4.x * inv, o4.y * inv, o4.z * inv, o4.w * inv));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// cross-attention against the query's encoder K/V
+// ------------------------------------------------------------------------------------------------------------
+constexpr int kXLd = 68;                                  // padded staged row (floats): conflict-free LDS.128 rows
+template <bool QS>                                        // QS: the beams' q rows are staged in shared memory too
+constexpr int x_warp_floats() { return 32 * kXLd + 32 * 64 + kXB * 32 + (QS ? kXB * 64 : 0); }   // K | V | exp | q
+
+__device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool on) {
+  const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d32), "l"(src), "r"(on ? 16 : 0) : "memory");
+}
+
+template <bool QS>
+__global__ void __launch_bounds__(kWarps * 32, QS ? 2 : 3) cross_attn_warp_kernel(CrossAttnArgs a, ActOut ctx) {
+  extern __shared__ __align__(16) float xsmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;
+  float* ks = xsmem + warp * x_warp_floats<QS>();
+  float* vs = ks + 32 * kXLd;                                      // unpadded: read as lane-contiguous float2
+  float* es = vs + 32 * 64;
+  float* qs = es + kXB * 32;
+  const int wid = blockIdx.x * kWarps + warp;
+  const int b = wid / a.H, h = wid - b * a.H;
+  const int rpq = a.rows_per_query, S = a.S;
+  pdl_wait();
+  if (b * rpq >= a.M) return;
+  const int inner = a.H * 64;
+  const int i0 = blockIdx.y * kXB;
+  const int nact = min(kXB, rpq - i0);
+  const int64_t row0 = (int64_t)b * rpq + i0;
+  const int64_t* mk = a.mask + (int64_t)b * S;
+  // q rows of this warp's beams -> shared memory (joins the first K commit group); rows beyond nact repeat row 0
+  const float* qg = a.q + row0 * inner + h * 64;
+  if (QS) {
+    const float* qb = qg + l16 * 4;
+#pragma unroll
+    for (int r = 0; r < kXB / 2; ++r) {
+      const int i = 2 * r + half;
+      cp_async16(qs + i * 64 + l16 * 4, qb + (int64_t)(i < nact ? i : 0) * inner, true);
+    }
+  }
+  // this lane's source pointer for staging: row (half) of the chunk, 16-byte column l16; advances 2 rows per step
+  const float* kv_lane = a.kv + ((int64_t)b * S + half) * a.ld + h * 64 + l16 * 4;
+  const int64_t step2 = 2 * a.ld;
+
+  float run_max[kXB], run_sum[kXB];
+  float2 o2[kXB];
+#pragma unroll
+  for (int i = 0; i < kXB; ++i) { run_max[i] = -INFINITY; run_sum[i] = 0.f; o2[i] = make_float2(0.f, 0.f); }
+
+  for (int c0 = 0; c0 < S; c0 += 32) {
+    const int p = c0 + lane;
+    const bool ok = p < S && mk[p < S ? p : 0] != 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, ok);
+    if (bits == 0) continue;                                       // warp-uniform: a fully masked chunk
+    if (c0 > 0) __syncwarp();                                      // previous chunk's readers are done with ks/vs/es
+    // ---- stage the chunk: 16 lanes x 16 B per row, two rows per instruction, zero fill for masked keys ---------
+    {
+      const float* src = kv_lane + (int64_t)c0 * a.ld + a.k_off;
+      const unsigned mybits = bits >> half;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const bool on = (mybits >> (2 * r)) & 1u;
+        cp_async16(ks + (2 * r + half) * kXLd + l16 * 4, on ? src : a.kv, on);
+        src += step2;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      src = kv_lane + (int64_t)c0 * a.ld + a.v_off;
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const bool on = (mybits >> (2 * r)) & 1u;
+        cp_async16(vs + (2 * r + half) * 64 + l16 * 4, on ? src : a.kv, on);
+        src += step2;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    // ---- scores: lane = key; the K row comes from shared memory once and meets every beam's q -----------------
+    float sc[kXB];
+#pragma unroll
+    for (int i = 0; i < kXB; ++i) sc[i] = 0.f;
+#pragma unroll 4
+    for (int j = 0; j < 16; ++j) {
+      const float4 k4 = *reinterpret_cast<const float4*>(ks + lane * kXLd + j * 4);
+#pragma unroll
+      for (int i = 0; i < kXB; ++i) {
+        const float4 q4 = QS ? *reinterpret_cast<const float4*>(qs + i * 64 + j * 4)
+                             : __ldg(reinterpret_cast<const float4*>(qg + (int64_t)(i < nact ? i : 0) * inner) + j);
+        sc[i] = dot4(q4, k4, sc[i]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kXB; ++i) {
+      const float s_i = ok ? sc[i] : -INFINITY;
+      const float new_max = fmaxf(run_max[i], warp_max(s_i));      // finite: the chunk has an unmasked key
+      const float rescale = expf(run_max[i] - new_max);
+      const float e = expf(s_i - new_max);                         // 0 for masked keys
+      run_max[i] = new_max;
+      run_sum[i] = run_sum[i] * rescale + warp_sum(e);
+      o2[i].x *= rescale;
+      o2[i].y *= rescale;
+      es[i * 32 + lane] = e;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- context: lane = a pair of output dims; 4 keys per iteration from shared memory ------------------------
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (((bits >> (4 * g)) & 0xFu) == 0) continue;               // warp-uniform
+      const float2 v0 = *reinterpret_cast<const float2*>(vs + (4 * g + 0) * 64 + lane * 2);
+      const float2 v1 = *reinterpret_cast<const float2*>(vs + (4 * g + 1) * 64 + lane * 2);
+      const float2 v2 = *reinterpret_cast<const float2*>(vs + (4 * g + 2) * 64 + lane * 2);
+      const float2 v3 = *reinterpret_cast<const float2*>(vs + (4 * g + 3) * 64 + lane * 2);
+#pragma unroll
+      for (int i = 0; i < kXB; ++i) {
+        const float4 e4 = *reinterpret_cast<const float4*>(es + i * 32 + 4 * g);
+        o2[i].x = fmaf(e4.x, v0.x, o2[i].x); o2[i].y = fmaf(e4.x, v0.y, o2[i].y);
+        o2[i].x = fmaf(e4.y, v1.x, o2[i].x); o2[i].y = fmaf(e4.y, v1.y, o2[i].y);
+        o2[i].x = fmaf(e4.z, v2.x, o2[i].x); o2[i].y = fmaf(e4.z, v2.y, o2[i].y);
+        o2[i].x = fmaf(e4.w, v3.x, o2[i].x); o2[i].y = fmaf(e4.w, v3.y, o2[i].y);
+      }
+    }
+  }
+  pdl_trigger();
+  asm volatile("cp.async.wait_group 0;" ::: "memory");             // (a fully masked query never waited for its q rows)
+#pragma unroll
+  for (int i = 0; i < kXB; ++i)
+    if (i < nact) {
+      const float inv = run_sum[i] > 0.f ? 1.0f / run_sum[i] : 0.f;
+      act_store2(ctx, (row0 + i) * inner + h * 64 + lane * 2, make_float2(o2[i].x * inv, o2[i].y * inv));
+    }
+}
+
+}  // namespace
+
+bool launch_self_attn_warp(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s, int* status) {
+  const dim3 grid(ceil_div((int64_t)a.M * a.H, kWarps)), block(kWarps * 32);
+  const cudaError_t err = launch_pdl(self_attn_warp_kernel, grid, block, 0, s, a, ctx);
+  *status = err == cudaSuccess ? 0 : fail(RB200_ERR_CUDA, "self_attn_warp_kernel launch: %s", cudaGetErrorString(err));
+  launch_count()++;
+  return true;
+}
+
+bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, int* status) {
+  const int B = a.M / a.rows_per_query;
+  const dim3 grid(ceil_div((int64_t)B * a.H, kWarps), ceil_div(a.rows_per_query, kXB)), block(kWarps * 32);
+  static const bool qs = []() {
+    const char* e = getenv("RB200_XATTN_Q");     // default: q rows staged in shared memory (24 us vs 30 us per launch)
+    return !(e && strcmp(e, "ldg") == 0);
+  }();
+  const size_t smem = (size_t)kWarps * (qs ? x_warp_floats<true>() : x_warp_floats<false>()) * sizeof(float);
+  auto kern = qs ? cross_attn_warp_kernel<true> : cross_attn_warp_kernel<false>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) {
+      *status = fail(RB200_ERR_CUDA, "cross_attn_warp_kernel attribute: %s", cudaGetErrorString(e));
+      return true;
+    }
+    attr_set = true;
+  }
+  const cudaError_t err = launch_pdl(kern, grid, block, smem, s, a, ctx);
+  *status = err == cudaSuccess ? 0 : fail(RB200_ERR_CUDA, "cross_attn_warp_kernel launch: %s", cudaGetErrorString(err));
+  launch_count()++;
+  return true;
+}
+
+}  // namespace rb

@@ -54,7 +54,6 @@ __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = a.nb, V = a.tv.V, words = a.tv.words, t = a.t;
   const int total = nb * V;
-  rb::pdl_trigger();
   rb::pdl_wait();
 
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -150,6 +149,7 @@ __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
     }
   }
 
+  rb::pdl_trigger();   // selection done; only the state write-back remains
   // ---- C. new beam state: scores, trie child, token history, KV ancestry, next decoder input --------
   for (int j = tid; j < nb; j += THREADS) {
     const int c = win_idx[j];

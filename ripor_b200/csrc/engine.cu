@@ -36,6 +36,30 @@ struct Layer {
 
 }  // namespace
 
+// One lane = the workspaces of one independent batch in flight. Queries never interact, so a large batch is split
+// over two lanes that run on two streams: while one lane drains a GEMM (epilogue, launch gap, a 60-of-74-SM-pair
+// tail) or sits in an HBM-bound attention kernel, the other lane's kernels fill the idle SMs / tensor pipes.
+struct Lane {
+  int64_t Mcap = 0, Rcap = 0, BScap = 0;
+  float* x = nullptr;              // [Mcap, d] residual stream
+  void* xn = nullptr;              // ActBuf [planes][Mcap][d]
+  float* qkv = nullptr;            // [Mcap, 3*inner]
+  float* q2 = nullptr;             // [Mcap, inner]
+  void* ctx = nullptr;             // ActBuf [planes][Mcap][inner]
+  void* hbuf = nullptr;            // ActBuf [planes][Mcap][dff]
+  float* logits = nullptr;         // [Rcap, V]
+  float* cross_kv = nullptr;       // [BScap, Nl*2*inner]
+  float* enc_out = nullptr;        // [BScap, d]
+  float* cache_k = nullptr;        // [Nl][Lmodel][Rcap][inner]
+  float* cache_v = nullptr;
+  rb200_beam* beam = nullptr;
+  cudaStream_t own_stream = nullptr;   // lane 1 only
+  cudaEvent_t done = nullptr;
+  // batch in flight
+  int B = 0, S = 0, nb = 0;
+  const int64_t* cur_mask = nullptr;
+};
+
 struct rb200_engine {
   rb200_engine_config cfg;
   int mode = 0, planes = 1, elem = 4;
@@ -54,29 +78,15 @@ struct rb200_engine {
   int enc_bias_S = 0;
   std::set<std::string> have;
   bool finalized = false;
-  // workspaces
-  int64_t Mcap = 0, Rcap = 0, BScap = 0;
-  float* x = nullptr;              // [Mcap, d] residual stream
-  void* xn = nullptr;              // ActBuf [planes][Mcap][d]
-  float* qkv = nullptr;            // [Mcap, 3*inner]
-  float* q2 = nullptr;             // [Mcap, inner]
-  void* ctx = nullptr;             // ActBuf [planes][Mcap][inner]
-  void* hbuf = nullptr;            // ActBuf [planes][Mcap][dff]
-  float* logits = nullptr;         // [Rcap, V]
-  float* cross_kv = nullptr;       // [BScap, Nl*2*inner]
-  float* enc_out = nullptr;        // [BScap, d]
-  float* cache_k = nullptr;        // [Nl][Lmodel][Rcap][inner]
-  float* cache_v = nullptr;
+  Lane lanes[2];                   // lane 0: full capacity; lane 1: the second half of a split batch
+  int num_lanes = 1;
+  cudaEvent_t fork = nullptr;
   int64_t* ids_dev = nullptr;      // host-call staging
   int64_t* mask_dev = nullptr;
   int64_t* seq_dev = nullptr;
   float* score_dev = nullptr;
   int32_t* leaf_dev = nullptr;
   int64_t ws_bytes = 0;
-  rb200_beam* beam = nullptr;
-  // batch in flight
-  int B = 0, S = 0, nb = 0;
-  const int64_t* cur_mask = nullptr;
   int64_t launches = 0;
   // optional per-GEMM event timing (rb200_engine_set_profiling)
   bool profiling = false;
@@ -86,7 +96,9 @@ struct rb200_engine {
 
   int* overflow = nullptr;         // device flags: [0] activation overflow of the batch in flight, [1] weights
 
-  ActOut act(void* base, int64_t row_len) const { return ActOut{base, Mcap * row_len, mode, overflow}; }
+  ActOut act(const Lane& l, void* base, int64_t row_len) const {
+    return ActOut{base, l.Mcap * row_len, mode, overflow};
+  }
 };
 
 namespace {
@@ -114,11 +126,11 @@ int copy_f32(float* dst, const float* src, int64_t n, cudaStream_t s) {
   return 0;
 }
 
-int gemm(rb200_engine* e, const void* A, int64_t a_row_len, const Packed& w, float* C, int64_t ldc, ActOut act,
-         int64_t M, int epi, cudaStream_t s) {
+int gemm(rb200_engine* e, const Lane& l, const void* A, int64_t a_row_len, const Packed& w, float* C, int64_t ldc,
+         ActOut act, int64_t M, int epi, cudaStream_t s) {
   GemmArgs g;
   g.mode = e->mode;
-  g.A = A; g.a_plane = e->Mcap * a_row_len;
+  g.A = A; g.a_plane = l.Mcap * a_row_len;
   g.W = w.ptr; g.w_plane = w.plane;
   g.C = C; g.ldc = ldc; g.act = act;
   g.M = M; g.N = w.N; g.K = w.K; g.epilogue = epi;
@@ -173,6 +185,8 @@ int build_bias_tables(rb200_engine* e, int S, cudaStream_t s) {
 
 }  // namespace
 
+namespace rb { void set_gemm_trace(unsigned long long* dev); }   // gemm_sm100_2cta.cu
+
 static float half_bits_to_float(uint16_t h) {
   const uint32_t sign = (uint32_t)(h & 0x8000u) << 16, exp = (h >> 10) & 0x1f, man = h & 0x3ffu;
   if (exp == 0) {
@@ -207,9 +221,6 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
   e->elem = rb::prec_elem_bytes(e->mode);
   e->d = cfg->d_model; e->H = cfg->num_heads; e->inner = cfg->num_heads * cfg->d_kv; e->dff = cfg->d_ff;
   e->V = cfg->decoder_vocab_size; e->Lmodel = cfg->docid_len;
-  e->Rcap = (int64_t)cfg->max_batch * cfg->max_beams;
-  e->BScap = (int64_t)cfg->max_batch * cfg->max_src_len;
-  e->Mcap = std::max(e->Rcap, e->BScap);
   const int d = e->d, inner = e->inner, dff = e->dff;
   e->enc.resize(cfg->num_layers);
   e->dec.resize(cfg->num_decoder_layers);
@@ -243,32 +254,49 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
   RB_TRY(dev_alloc(e, (void**)&e->start_emb, d * 4));
   RB_TRY(dev_alloc(e, (void**)&e->enc_final_ln, d * 4));
   RB_TRY(dev_alloc(e, (void**)&e->dec_final_ln, d * 4));
-  // workspaces
+  // workspaces: lane 0 can hold a whole batch, lane 1 the second half of a split one
   const int64_t pe = (int64_t)e->planes * e->elem;
-  RB_TRY(dev_alloc(e, (void**)&e->x, e->Mcap * d * 4));
-  RB_TRY(dev_alloc(e, &e->xn, e->Mcap * d * pe));
-  RB_TRY(dev_alloc(e, (void**)&e->qkv, e->Mcap * 3 * inner * 4));
-  RB_TRY(dev_alloc(e, (void**)&e->q2, e->Mcap * inner * 4));
-  RB_TRY(dev_alloc(e, &e->ctx, e->Mcap * inner * pe));
-  RB_TRY(dev_alloc(e, &e->hbuf, e->Mcap * dff * pe));
-  RB_TRY(dev_alloc(e, (void**)&e->logits, e->Rcap * e->V * 4));
-  RB_TRY(dev_alloc(e, (void**)&e->cross_kv, e->BScap * cfg->num_decoder_layers * 2 * inner * 4));
-  RB_TRY(dev_alloc(e, (void**)&e->enc_out, e->BScap * d * 4));
-  const int64_t cache = (int64_t)cfg->num_decoder_layers * e->Lmodel * e->Rcap * inner * 4;
-  RB_TRY(dev_alloc(e, (void**)&e->cache_k, cache));
-  RB_TRY(dev_alloc(e, (void**)&e->cache_v, cache));
-  RB_TRY(dev_alloc(e, (void**)&e->ids_dev, e->BScap * 8));
-  RB_TRY(dev_alloc(e, (void**)&e->mask_dev, e->BScap * 8));
-  RB_TRY(dev_alloc(e, (void**)&e->seq_dev, e->Rcap * (e->Lmodel + 1) * 8));
-  RB_TRY(dev_alloc(e, (void**)&e->score_dev, e->Rcap * 4));
-  RB_TRY(dev_alloc(e, (void**)&e->leaf_dev, e->Rcap * 2 * 4));
+  {
+    const char* env = getenv("RB200_LANES");
+    // measured on B200 (bench workload): two lanes 2507 q/s vs one lane 2562 q/s - the GEMMs are already bound by
+    // L2->SM operand delivery, so overlapping a second batch only adds contention. Opt-in with RB200_LANES=2.
+    e->num_lanes = (cfg->max_batch >= 2 && env && env[0] == '2') ? 2 : 1;
+  }
+  for (int li = 0; li < e->num_lanes; ++li) {
+    Lane& l = e->lanes[li];
+    const int lane_batch = li == 0 ? cfg->max_batch : cfg->max_batch / 2;
+    l.Rcap = (int64_t)lane_batch * cfg->max_beams;
+    l.BScap = (int64_t)lane_batch * cfg->max_src_len;
+    l.Mcap = std::max(l.Rcap, l.BScap);
+    RB_TRY(dev_alloc(e, (void**)&l.x, l.Mcap * d * 4));
+    RB_TRY(dev_alloc(e, &l.xn, l.Mcap * d * pe));
+    RB_TRY(dev_alloc(e, (void**)&l.qkv, l.Mcap * 3 * inner * 4));
+    RB_TRY(dev_alloc(e, (void**)&l.q2, l.Mcap * inner * 4));
+    RB_TRY(dev_alloc(e, &l.ctx, l.Mcap * inner * pe));
+    RB_TRY(dev_alloc(e, &l.hbuf, l.Mcap * dff * pe));
+    RB_TRY(dev_alloc(e, (void**)&l.logits, l.Rcap * e->V * 4));
+    RB_TRY(dev_alloc(e, (void**)&l.cross_kv, l.BScap * cfg->num_decoder_layers * 2 * inner * 4));
+    RB_TRY(dev_alloc(e, (void**)&l.enc_out, l.BScap * d * 4));
+    const int64_t cache = (int64_t)cfg->num_decoder_layers * e->Lmodel * l.Rcap * inner * 4;
+    RB_TRY(dev_alloc(e, (void**)&l.cache_k, cache));
+    RB_TRY(dev_alloc(e, (void**)&l.cache_v, cache));
+    // planes of the activation buffers may be read past M by TMA boxes: start from defined contents
+    RB_CUDA(cudaMemset(l.xn, 0, (size_t)(l.Mcap * d * pe)));
+    RB_CUDA(cudaMemset(l.ctx, 0, (size_t)(l.Mcap * inner * pe)));
+    RB_CUDA(cudaMemset(l.hbuf, 0, (size_t)(l.Mcap * dff * pe)));
+    RB_TRY(rb200_beam_create(cfg->device, lane_batch, cfg->max_beams, e->Lmodel, e->V, &l.beam));
+    RB_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+    if (li > 0) RB_CUDA(cudaStreamCreateWithFlags(&l.own_stream, cudaStreamNonBlocking));
+  }
+  RB_CUDA(cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming));
+  const int64_t Rall = (int64_t)cfg->max_batch * cfg->max_beams, BSall = (int64_t)cfg->max_batch * cfg->max_src_len;
+  RB_TRY(dev_alloc(e, (void**)&e->ids_dev, BSall * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->mask_dev, BSall * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->seq_dev, Rall * (e->Lmodel + 1) * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->score_dev, Rall * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->leaf_dev, Rall * 2 * 4));
   RB_TRY(dev_alloc(e, (void**)&e->overflow, 2 * 4));
   RB_CUDA(cudaMemset(e->overflow, 0, 8));
-  // planes of the activation buffers may be read past M by TMA boxes: start from defined contents
-  RB_CUDA(cudaMemset(e->xn, 0, (size_t)(e->Mcap * d * pe)));
-  RB_CUDA(cudaMemset(e->ctx, 0, (size_t)(e->Mcap * inner * pe)));
-  RB_CUDA(cudaMemset(e->hbuf, 0, (size_t)(e->Mcap * dff * pe)));
-  RB_TRY(rb200_beam_create(cfg->device, cfg->max_batch, cfg->max_beams, e->Lmodel, e->V, &e->beam));
   *out = e;
   return 0;
 }
@@ -284,11 +312,17 @@ int rb200_engine_free(rb200_engine* e) {
   fp(e->ckv);
   for (auto& p : e->out_tab) fp(p);
   for (auto p : e->in_tab) cudaFree(p);
-  void* bufs[] = {e->shared_emb, e->start_emb, e->enc_final_ln, e->dec_final_ln, e->dec_bias, e->enc_bias, e->x,
-                  e->xn, e->qkv, e->q2, e->ctx, e->hbuf, e->logits, e->cross_kv, e->enc_out, e->cache_k, e->cache_v,
+  void* bufs[] = {e->shared_emb, e->start_emb, e->enc_final_ln, e->dec_final_ln, e->dec_bias, e->enc_bias,
                   e->ids_dev, e->mask_dev, e->seq_dev, e->score_dev, e->leaf_dev, e->overflow};
   for (void* b : bufs) cudaFree(b);
-  rb200_beam_free(e->beam);
+  for (Lane& l : e->lanes) {
+    void* lb[] = {l.x, l.xn, l.qkv, l.q2, l.ctx, l.hbuf, l.logits, l.cross_kv, l.enc_out, l.cache_k, l.cache_v};
+    for (void* b : lb) cudaFree(b);
+    rb200_beam_free(l.beam);
+    if (l.done) cudaEventDestroy(l.done);
+    if (l.own_stream) cudaStreamDestroy(l.own_stream);
+  }
+  if (e->fork) cudaEventDestroy(e->fork);
   for (auto ev : e->events) cudaEventDestroy(ev);
   delete e;
   return 0;
@@ -426,6 +460,76 @@ int rb200_engine_finalize_weights(rb200_engine* e, void* stream) {
   return 0;
 }
 
+}  // extern "C"
+
+namespace {
+
+int lane_encode(rb200_engine* e, Lane& l, const int64_t* ids, const int64_t* mask, int batch, int S, int num_beams,
+                cudaStream_t s) {
+  l.B = batch; l.S = S; l.nb = num_beams; l.cur_mask = mask;
+  const int64_t rows = (int64_t)batch * S;
+  const int d = e->d, inner = e->inner, dff = e->dff;
+  const float eps = e->cfg.layer_norm_eps;
+  RB_TRY(rb::launch_embed_rows(e->shared_emb, ids, l.x, rows, d, s));
+  for (auto& w : e->enc) {
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln0, e->act(l, l.xn, d), rows, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, rows, rb::EPI_STORE, s));
+    rb::EncAttnArgs ea{l.qkv, mask, e->enc_bias, batch, S, e->H};
+    RB_TRY(rb::launch_enc_attn(ea, e->act(l, l.ctx, inner), s));
+    RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, rows, rb::EPI_RESIDUAL, s));
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), rows, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), rows, rb::EPI_RELU_ACT, s));
+    RB_TRY(gemm(e, l, l.hbuf, dff, w.wo, l.x, d, ActOut{}, rows, rb::EPI_RESIDUAL, s));
+  }
+  RB_TRY(rb::launch_rmsnorm_f32(l.x, e->enc_final_ln, l.enc_out, rows, d, eps, s));
+  RB_TRY(rb::launch_rmsnorm(l.x, e->enc_final_ln, e->act(l, l.xn, d), rows, d, eps, 1.0f, s));
+  // cross-attention K/V of every decoder layer in one GEMM: [B*S, d] x [d, Nl*2*inner]
+  RB_TRY(gemm(e, l, l.xn, d, e->ckv, l.cross_kv, e->ckv.N, ActOut{}, rows, rb::EPI_STORE, s));
+  return 0;
+}
+
+int lane_decode_step(rb200_engine* e, Lane& l, const rb200_beam* beam, int t, float* logits, cudaStream_t s) {
+  const int rpq = (t == 0) ? 1 : l.nb;
+  const int64_t M = (int64_t)l.B * rpq;
+  const int d = e->d, inner = e->inner, dff = e->dff;
+  const float eps = e->cfg.layer_norm_eps;
+  if (t == 0) {
+    RB_TRY(rb::launch_broadcast_row(e->start_emb, l.x, M, d, s));
+  }
+  const int64_t layer_cache = (int64_t)e->Lmodel * l.Rcap * inner;
+  const int64_t ckv_ld = e->ckv.N;
+  for (size_t i = 0; i < e->dec.size(); ++i) {
+    Layer& w = e->dec[i];
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln0, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
+    rb::SelfAttnArgs sa;
+    sa.qkv = l.qkv; sa.cache_k = l.cache_k + i * layer_cache; sa.cache_v = l.cache_v + i * layer_cache;
+    sa.anc = beam->anc[beam->cur]; sa.bias = e->dec_bias; sa.row_cap = l.Rcap;
+    sa.M = (int)M; sa.H = e->H; sa.L = e->Lmodel; sa.t = t; sa.rpq = rpq; sa.nb = l.nb;
+    RB_TRY(rb::launch_self_attn_decode(sa, e->act(l, l.ctx, inner), s));
+    RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
+    rb::CrossAttnArgs ca;
+    ca.q = l.q2; ca.kv = l.cross_kv; ca.ld = ckv_ld; ca.k_off = (int64_t)(i * 2) * inner;
+    ca.v_off = (int64_t)(i * 2 + 1) * inner; ca.mask = l.cur_mask; ca.M = (int)M; ca.H = e->H; ca.S = l.S;
+    ca.rows_per_query = rpq;
+    RB_TRY(rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s));
+    RB_TRY(gemm(e, l, l.ctx, inner, w.co, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln2, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), M, rb::EPI_RELU_ACT, s));
+    RB_TRY(gemm(e, l, l.hbuf, dff, w.wo, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+  }
+  const float scale = e->cfg.scaleup_output_hidden ? 1.0f / sqrtf((float)d) : 1.0f;
+  RB_TRY(rb::launch_rmsnorm(l.x, e->dec_final_ln, e->act(l, l.xn, d), M, d, eps, scale, s));
+  RB_TRY(gemm(e, l, l.xn, d, e->out_tab[t], logits, e->V, ActOut{}, M, rb::EPI_STORE, s));
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
 int rb200_engine_encode(rb200_engine* e, const int64_t* ids, const int64_t* mask, int batch, int S, int num_beams,
                         void* stream) {
   RB_REQUIRE(e && ids && mask, "null argument");
@@ -437,82 +541,29 @@ int rb200_engine_encode(rb200_engine* e, const int64_t* ids, const int64_t* mask
   cudaStream_t s = (cudaStream_t)stream;
   RB_CUDA(cudaSetDevice(e->cfg.device));
   RB_TRY(build_bias_tables(e, S, s));
-  e->B = batch; e->S = S; e->nb = num_beams; e->cur_mask = mask;
-  const int64_t rows = (int64_t)batch * S;
-  const int d = e->d, inner = e->inner, dff = e->dff;
-  const float eps = e->cfg.layer_norm_eps;
-  RB_TRY(rb::launch_embed_rows(e->shared_emb, ids, e->x, rows, d, s));
-  for (auto& l : e->enc) {
-    RB_TRY(rb::launch_rmsnorm(e->x, l.ln0, e->act(e->xn, d), rows, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, e->xn, d, l.qkv, e->qkv, 3 * inner, ActOut{}, rows, rb::EPI_STORE, s));
-    rb::EncAttnArgs ea{e->qkv, mask, e->enc_bias, batch, S, e->H};
-    RB_TRY(rb::launch_enc_attn(ea, e->act(e->ctx, inner), s));
-    RB_TRY(gemm(e, e->ctx, inner, l.o, e->x, d, ActOut{}, rows, rb::EPI_RESIDUAL, s));
-    RB_TRY(rb::launch_rmsnorm(e->x, l.ln1, e->act(e->xn, d), rows, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, e->xn, d, l.wi, nullptr, 0, e->act(e->hbuf, dff), rows, rb::EPI_RELU_ACT, s));
-    RB_TRY(gemm(e, e->hbuf, dff, l.wo, e->x, d, ActOut{}, rows, rb::EPI_RESIDUAL, s));
-  }
-  RB_TRY(rb::launch_rmsnorm_f32(e->x, e->enc_final_ln, e->enc_out, rows, d, eps, s));
-  RB_TRY(rb::launch_rmsnorm(e->x, e->enc_final_ln, e->act(e->xn, d), rows, d, eps, 1.0f, s));
-  // cross-attention K/V of every decoder layer in one GEMM: [B*S, d] x [d, Nl*2*inner]
-  RB_TRY(gemm(e, e->xn, d, e->ckv, e->cross_kv, e->ckv.N, ActOut{}, rows, rb::EPI_STORE, s));
-  return 0;
+  return lane_encode(e, e->lanes[0], ids, mask, batch, S, num_beams, s);
 }
 
 int rb200_engine_encoder_states(const rb200_engine* e, const float** states) {
   RB_REQUIRE(e && states, "null argument");
-  *states = e->enc_out;
+  *states = e->lanes[0].enc_out;
   return 0;
 }
 
 int rb200_engine_decode_step(rb200_engine* e, const rb200_beam* beam, int t, float* logits, void* stream) {
   RB_REQUIRE(e && beam && logits, "null argument");
-  if (e->B < 1) return rb::fail(RB200_ERR_STATE, "rb200_engine_encode has not been called");
+  Lane& l = e->lanes[0];
+  if (l.B < 1) return rb::fail(RB200_ERR_STATE, "rb200_engine_encode has not been called");
   RB_REQUIRE(t >= 0 && t < e->Lmodel, "position %d outside [0, %d)", t, e->Lmodel);
   RB_REQUIRE(beam->step == t, "beam state is at step %d, decoder asked for position %d", beam->step, t);
-  RB_REQUIRE(beam->nb == e->nb && beam->batch == e->B, "beam state shape differs from the encoded batch");
+  RB_REQUIRE(beam->nb == l.nb && beam->batch == l.B, "beam state shape differs from the encoded batch");
   RB_REQUIRE(beam->L == e->Lmodel, "beam state L=%d differs from the model's docid_len=%d", beam->L, e->Lmodel);
-  cudaStream_t s = (cudaStream_t)stream;
-  const int rpq = (t == 0) ? 1 : e->nb;
-  const int64_t M = (int64_t)e->B * rpq;
-  const int d = e->d, inner = e->inner, dff = e->dff;
-  const float eps = e->cfg.layer_norm_eps;
-  if (t == 0) {
-    RB_TRY(rb::launch_broadcast_row(e->start_emb, e->x, M, d, s));
-  }
-  const int64_t layer_cache = (int64_t)e->Lmodel * e->Rcap * inner;
-  const int64_t ckv_ld = e->ckv.N;
-  for (size_t i = 0; i < e->dec.size(); ++i) {
-    Layer& l = e->dec[i];
-    RB_TRY(rb::launch_rmsnorm(e->x, l.ln0, e->act(e->xn, d), M, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, e->xn, d, l.qkv, e->qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
-    rb::SelfAttnArgs sa;
-    sa.qkv = e->qkv; sa.cache_k = e->cache_k + i * layer_cache; sa.cache_v = e->cache_v + i * layer_cache;
-    sa.anc = beam->anc[beam->cur]; sa.bias = e->dec_bias; sa.row_cap = e->Rcap;
-    sa.M = (int)M; sa.H = e->H; sa.L = e->Lmodel; sa.t = t; sa.rpq = rpq; sa.nb = e->nb;
-    RB_TRY(rb::launch_self_attn_decode(sa, e->act(e->ctx, inner), s));
-    RB_TRY(gemm(e, e->ctx, inner, l.o, e->x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
-    RB_TRY(rb::launch_rmsnorm(e->x, l.ln1, e->act(e->xn, d), M, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, e->xn, d, l.cq, e->q2, inner, ActOut{}, M, rb::EPI_STORE, s));
-    rb::CrossAttnArgs ca;
-    ca.q = e->q2; ca.kv = e->cross_kv; ca.ld = ckv_ld; ca.k_off = (int64_t)(i * 2) * inner;
-    ca.v_off = (int64_t)(i * 2 + 1) * inner; ca.mask = e->cur_mask; ca.M = (int)M; ca.H = e->H; ca.S = e->S;
-    ca.rows_per_query = rpq;
-    RB_TRY(rb::launch_cross_attn_decode(ca, e->act(e->ctx, inner), s));
-    RB_TRY(gemm(e, e->ctx, inner, l.co, e->x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
-    RB_TRY(rb::launch_rmsnorm(e->x, l.ln2, e->act(e->xn, d), M, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, e->xn, d, l.wi, nullptr, 0, e->act(e->hbuf, dff), M, rb::EPI_RELU_ACT, s));
-    RB_TRY(gemm(e, e->hbuf, dff, l.wo, e->x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
-  }
-  const float scale = e->cfg.scaleup_output_hidden ? 1.0f / sqrtf((float)d) : 1.0f;
-  RB_TRY(rb::launch_rmsnorm(e->x, e->dec_final_ln, e->act(e->xn, d), M, d, eps, scale, s));
-  RB_TRY(gemm(e, e->xn, d, e->out_tab[t], logits, e->V, ActOut{}, M, rb::EPI_STORE, s));
-  return 0;
+  return lane_decode_step(e, l, beam, t, logits, (cudaStream_t)stream);
 }
 
 int rb200_engine_beam(rb200_engine* e, rb200_beam** beam) {
   RB_REQUIRE(e && beam, "null argument");
-  *beam = e->beam;
+  *beam = e->lanes[0].beam;
   return 0;
 }
 
@@ -522,6 +573,9 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
                         int S, int num_beams, int max_new_tokens, int num_return, int apply_log_softmax,
                         int64_t* sequences, float* scores, int32_t* leaf, void* stream) {
   RB_REQUIRE(e && trie && ids && mask && sequences && scores, "null argument");
+  if (!e->finalized) return rb::fail(RB200_ERR_STATE, "weights not finalized: call rb200_engine_finalize_weights");
+  RB_REQUIRE(batch >= 1 && batch <= e->cfg.max_batch, "batch %d outside [1, %d]", batch, e->cfg.max_batch);
+  RB_REQUIRE(S >= 1 && S <= e->cfg.max_src_len, "source length %d outside [1, %d]", S, e->cfg.max_src_len);
   RB_REQUIRE(num_beams == e->cfg.max_beams, "the engine was created for num_beams=%d, got %d", e->cfg.max_beams,
              num_beams);
   RB_REQUIRE(max_new_tokens >= 1 && max_new_tokens <= e->Lmodel && max_new_tokens <= trie->L,
@@ -529,20 +583,49 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
   RB_REQUIRE(num_return >= 1 && num_return <= num_beams,
              "`num_return_sequences` has to be smaller or equal to `num_beams`.");
   RB_REQUIRE(trie->V == e->V, "trie V=%d but the model's decoder_vocab_size is %d", trie->V, e->V);
+  cudaStream_t s0 = (cudaStream_t)stream;
+  RB_CUDA(cudaSetDevice(e->cfg.device));
   const int64_t launches0 = rb::launch_count();
-  RB_CUDA(cudaMemsetAsync(e->overflow, 0, 4, (cudaStream_t)stream));
-  RB_TRY(rb200_engine_encode(e, ids, mask, batch, S, num_beams, stream));
-  RB_TRY(rb200_beam_reset(e->beam, trie, batch, stream));
-  for (int t = 0; t < max_new_tokens; ++t) {
-    RB_TRY(rb200_engine_decode_step(e, e->beam, t, e->logits, stream));
-    const bool more = t + 1 < max_new_tokens;
-    RB_TRY(rb200_beam_step(e->beam, trie, e->logits, t == 0 ? 1 : num_beams, apply_log_softmax,
-                           more ? e->in_tab[t] : nullptr, more ? e->x : nullptr, e->d, stream));
+  RB_CUDA(cudaMemsetAsync(e->overflow, 0, 4, s0));
+  RB_TRY(build_bias_tables(e, S, s0));
+  // Split the batch over the two lanes when it is large enough to keep both busy (the profiling pass keeps one
+  // lane so that the per-GEMM event times are not inflated by the other lane's kernels).
+  const bool split = e->num_lanes == 2 && !e->profiling && batch >= 16 && batch / 2 <= e->cfg.max_batch / 2;
+  const int nl = split ? 2 : 1;
+  int q0[3] = {0, split ? (batch + 1) / 2 : batch, batch};
+  if (split && batch - q0[1] > e->cfg.max_batch / 2) q0[1] = batch - e->cfg.max_batch / 2;
+  cudaStream_t ls[2] = {s0, e->lanes[1].own_stream};
+  if (split) {
+    RB_CUDA(cudaEventRecord(e->fork, s0));
+    RB_CUDA(cudaStreamWaitEvent(ls[1], e->fork, 0));
   }
-  RB_TRY(rb200_beam_finalize(e->beam, trie, num_return, 1.0, sequences, scores, leaf, stream));
+  for (int li = 0; li < nl; ++li) {
+    Lane& l = e->lanes[li];
+    const int nq = q0[li + 1] - q0[li];
+    RB_TRY(lane_encode(e, l, ids + (int64_t)q0[li] * S, mask + (int64_t)q0[li] * S, nq, S, num_beams, ls[li]));
+    RB_TRY(rb200_beam_reset(l.beam, trie, nq, ls[li]));
+  }
+  for (int t = 0; t < max_new_tokens; ++t) {
+    const bool more = t + 1 < max_new_tokens;
+    for (int li = 0; li < nl; ++li) {
+      Lane& l = e->lanes[li];
+      RB_TRY(lane_decode_step(e, l, l.beam, t, l.logits, ls[li]));
+      RB_TRY(rb200_beam_step(l.beam, trie, l.logits, t == 0 ? 1 : num_beams, apply_log_softmax,
+                             more ? e->in_tab[t] : nullptr, more ? l.x : nullptr, e->d, ls[li]));
+    }
+  }
+  for (int li = 0; li < nl; ++li) {
+    const int64_t o = (int64_t)q0[li] * num_return;
+    RB_TRY(rb200_beam_finalize(e->lanes[li].beam, trie, num_return, 1.0, sequences + o * (max_new_tokens + 1),
+                               scores + o, leaf ? leaf + o * 2 : nullptr, ls[li]));
+  }
+  if (split) {
+    RB_CUDA(cudaEventRecord(e->lanes[1].done, ls[1]));
+    RB_CUDA(cudaStreamWaitEvent(s0, e->lanes[1].done, 0));
+  }
   if (rb::prec_is_fp16(e->mode)) {
     const int n = batch * num_return;
-    poison_on_overflow_kernel<<<rb::ceil_div(n, 256), 256, 0, (cudaStream_t)stream>>>(scores, n, e->overflow);
+    poison_on_overflow_kernel<<<rb::ceil_div(n, 256), 256, 0, s0>>>(scores, n, e->overflow);
     RB_CUDA(cudaGetLastError());
     rb::launch_count()++;
   }
@@ -650,6 +733,82 @@ int rb200_gemm(int precision, const float* A, const float* W, float* C, int64_t 
   if (st == 0) {
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return rb::fail(RB200_ERR_CUDA, "rb200_gemm: %s", cudaGetErrorString(err));
+  }
+  return st;
+}
+
+int rb200_gemm_bench(int precision, int64_t M, int64_t N, int64_t K, int epilogue, int iters, int rotate_mb,
+                     double* avg_us, void* stream) {
+  RB_REQUIRE(avg_us && iters >= 1 && M >= 1 && N >= 1 && K >= 1, "bad argument");
+  RB_REQUIRE(precision >= 0 && precision <= 5 && epilogue >= 0 && epilogue <= 2, "unknown precision / epilogue");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int planes = rb::prec_planes(precision), elem = rb::prec_elem_bytes(precision);
+  const size_t a_bytes = (size_t)planes * M * K * elem, w_bytes = (size_t)planes * N * K * elem;
+  const size_t c_bytes = (size_t)M * N * 4, r_bytes = (size_t)planes * M * N * elem;
+  const size_t per = a_bytes + w_bytes + c_bytes + r_bytes;
+  int nbuf = (int)(((size_t)rotate_mb << 20) / per) + 1;
+  if (nbuf > 64) nbuf = 64;
+  std::vector<char*> bufs(nbuf, nullptr);
+  int st = 0;
+  for (int i = 0; i < nbuf && st == 0; ++i) {
+    if (cudaMalloc((void**)&bufs[i], per + 4096) != cudaSuccess) st = rb::fail(RB200_ERR_NOMEM, "cudaMalloc failed");
+    else cudaMemsetAsync(bufs[i], 0, per + 4096, s);   // zeros: valid in every plane format
+  }
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  auto run = [&](int i) {
+    char* b = bufs[i % nbuf];
+    GemmArgs g;
+    g.mode = precision; g.A = b; g.a_plane = M * K; g.W = b + a_bytes; g.w_plane = N * K;
+    g.C = reinterpret_cast<float*>(b + a_bytes + w_bytes); g.ldc = N; g.M = M; g.N = N; g.K = K;
+    g.epilogue = epilogue; g.out_scale = 1.0f;
+    g.act = epilogue == rb::EPI_RELU_ACT ? ActOut{b + a_bytes + w_bytes + c_bytes, M * N, precision, nullptr} : ActOut{};
+    return rb::launch_gemm(g, s);
+  };
+  for (int i = 0; i < nbuf + 3 && st == 0; ++i) st = run(i);
+  if (st == 0) {
+    cudaEventRecord(e0, s);
+    for (int i = 0; i < iters && st == 0; ++i) st = run(i);
+    cudaEventRecord(e1, s);
+    cudaStreamSynchronize(s);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *avg_us = (double)ms * 1e3 / iters;
+    if (getenv("RB200_GEMM_TRACE")) {   // one more launch with %globaltimer stamps per CTA; printed to stderr
+      unsigned long long* tr = nullptr;
+      const int slots = 160 * 8;
+      cudaMalloc((void**)&tr, slots * 8);
+      cudaMemsetAsync(tr, 0, slots * 8, s);
+      rb::set_gemm_trace(tr);
+      run(0);
+      run(1);
+      rb::set_gemm_trace(nullptr);
+      cudaStreamSynchronize(s);
+      std::vector<unsigned long long> h(slots);
+      cudaMemcpy(h.data(), tr, slots * 8, cudaMemcpyDeviceToHost);
+      cudaFree(tr);
+      unsigned long long base = ~0ull;
+      for (int c = 0; c < 160; ++c) if (h[c * 8] && h[c * 8] < base) base = h[c * 8];
+      const char* names[7] = {"entry", "prologue done", "first stage full", "last MMA commit", "accumulator ready",
+                              "epilogue done", "exit"};
+      for (int k = 0; k < 7; ++k) {
+        double sum = 0, mx = 0, mn = 1e30; int n = 0;
+        for (int c = 0; c < 160; ++c) if (h[c * 8 + k]) {
+          const double v = (double)(h[c * 8 + k] - base) / 1e3;
+          sum += v; mx = v > mx ? v : mx; mn = v < mn ? v : mn; ++n;
+        }
+        if (n) fprintf(stderr, "  trace %-18s n=%3d  min %7.2f  avg %7.2f  max %7.2f us\n", names[k], n, mn, sum / n, mx);
+      }
+    }
+  }
+  cudaStreamSynchronize(s);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  for (char* b : bufs) cudaFree(b);
+  if (st == 0) {
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return rb::fail(RB200_ERR_CUDA, "rb200_gemm_bench: %s", cudaGetErrorString(err));
   }
   return st;
 }

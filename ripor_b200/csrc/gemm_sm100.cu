@@ -271,10 +271,10 @@ PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
 
 struct MapKey {
   const void* ptr;
-  int64_t rows, k;
+  int64_t rows, k, ld;
   int box_rows, elem;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && k == o.k && box_rows == o.box_rows && elem == o.elem;
+    return ptr == o.ptr && rows == o.rows && k == o.k && ld == o.ld && box_rows == o.box_rows && elem == o.elem;
   }
 };
 struct MapKeyHash {
@@ -282,15 +282,20 @@ struct MapKeyHash {
     size_t h = std::hash<const void*>()(k.ptr);
     h = h * 1000003u ^ std::hash<int64_t>()(k.rows);
     h = h * 1000003u ^ std::hash<int64_t>()(k.k);
+    h = h * 1000003u ^ std::hash<int64_t>()(k.ld);
     h = h * 1000003u ^ (size_t)(k.box_rows * 8 + k.elem);
     return h;
   }
 };
 
-int get_tensor_map(const void* ptr, int64_t rows, int64_t k, int box_rows, int elem, CUtensorMap* out) {
+// 2-D row-major tensor [rows, k] with row stride `ld` elements; boxes of box_rows x 128 bytes, SWIZZLE_128B.
+// Used for the operand loads (ld == k) and for the epilogue's TMA stores / reduce-adds of output tiles.
+int get_tensor_map(const void* ptr, int64_t rows, int64_t k, int box_rows, int elem, CUtensorMap* out,
+                   int64_t ld = 0) {
   static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
   static std::mutex mu;
-  const MapKey key{ptr, rows, k, box_rows, elem};
+  if (ld == 0) ld = k;
+  const MapKey key{ptr, rows, k, ld, box_rows, elem};
   {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find(key);
@@ -299,7 +304,7 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t k, int box_rows, int e
   auto encode = get_encode_fn();
   if (!encode) return fail(RB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
   const cuuint64_t gdim[2] = {(cuuint64_t)k, (cuuint64_t)rows};
-  const cuuint64_t gstride[1] = {(cuuint64_t)k * elem};
+  const cuuint64_t gstride[1] = {(cuuint64_t)ld * elem};
   const cuuint32_t box[2] = {(cuuint32_t)(SWIZZLE_BYTES / elem), (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
@@ -308,8 +313,8 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t k, int box_rows, int e
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
-    return fail(RB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for ptr=%p rows=%lld k=%lld box_rows=%d elem=%d",
-                (int)r, ptr, (long long)rows, (long long)k, box_rows, elem);
+    return fail(RB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for ptr=%p rows=%lld k=%lld ld=%lld box_rows=%d elem=%d",
+                (int)r, ptr, (long long)rows, (long long)k, (long long)ld, box_rows, elem);
   {
     std::lock_guard<std::mutex> lock(mu);
     cache[key] = m;
@@ -357,8 +362,8 @@ int launch_bn(const GemmArgs& g, cudaStream_t s) {
 }  // namespace
 
 // shared with gemm_sm100_2cta.cu
-int tensor_map_2d(const void* ptr, int64_t rows, int64_t k, int box_rows, int elem, CUtensorMap* out) {
-  return get_tensor_map(ptr, rows, k, box_rows, elem, out);
+int tensor_map_2d(const void* ptr, int64_t rows, int64_t k, int box_rows, int elem, CUtensorMap* out, int64_t ld) {
+  return get_tensor_map(ptr, rows, k, box_rows, elem, out, ld);
 }
 
 int launch_gemm_sm100_2cta(const GemmArgs& g, cudaStream_t s);

@@ -23,16 +23,17 @@
 
 namespace rb {
 
-int tensor_map_2d(const void* ptr, int64_t rows, int64_t k, int box_rows, int elem, CUtensorMap* out);
+static unsigned long long* g_gemm_trace = nullptr;     // device buffer [grid][8] or null
+void set_gemm_trace(unsigned long long* dev) { g_gemm_trace = dev; }
+
+int tensor_map_2d(const void* ptr, int64_t rows, int64_t k, int box_rows, int elem, CUtensorMap* out, int64_t ld);
 
 namespace {
 
 constexpr int BM = 128;                  // rows per CTA (256 per pair)
 constexpr int SWIZZLE_BYTES = 128;
-constexpr int kThreads = 192;
+constexpr int kThreads = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr uint32_t kSmemBudget = 227 * 1024;
-constexpr int kStgLd = 36;                               // padded row of the epilogue transpose tile (floats)
-constexpr uint32_t kStgBytes = 4 * 32 * kStgLd * 4;      // one 32 x 36 fp32 tile per epilogue warp
 constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // shared::cluster address of the same offset in the even (leader) CTA
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -133,6 +134,18 @@ __host__ __device__ constexpr uint32_t make_idesc_pair(int fmt, int n) {
          ((uint32_t)(256 >> 4) << 24);
 }
 
+// optional phase trace (tools/gemm_bench.py --trace): %globaltimer stamps per CTA, 8 slots each
+__device__ __forceinline__ void trace_stamp(unsigned long long* trace, int slot) {
+  if (trace) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    trace[blockIdx.x * 8 + slot] = t;
+  }
+}
+
+constexpr int kEpiWarps = 8;                             // two per TMEM lane quarter, each owning half of the columns
+constexpr uint32_t kEpiTile = 32 * SWIZZLE_BYTES;        // one 32-row x 128-byte staging tile per epilogue warp
+
 template <int ELEM_BYTES, int NTERMS, int BN>
 struct Cfg2 {
   static constexpr int PLANES = NTERMS == 3 ? 2 : 1;
@@ -141,22 +154,59 @@ struct Cfg2 {
   static constexpr uint32_t A_TILE = BM * SWIZZLE_BYTES;            // this CTA's 128 rows of A
   static constexpr uint32_t W_TILE = (BN / 2) * SWIZZLE_BYTES;      // this CTA's half of the W tile
   static constexpr uint32_t STAGE = PLANES * (A_TILE + W_TILE);
-  static constexpr int STAGES_RAW = (kSmemBudget - 2048 - kStgBytes) / STAGE;
+  static constexpr uint32_t EPI_BYTES = kEpiWarps * kEpiTile;
+  static constexpr int STAGES_RAW = (kSmemBudget - 2048 - EPI_BYTES) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
-  static constexpr uint32_t SMEM = STAGES * STAGE + 1024 + 256 + kStgBytes;
+  static constexpr uint32_t SMEM = STAGES * STAGE + EPI_BYTES + 1024 + 256;
   static constexpr int TMEM_COLS = 2 * BN;                           // double-buffered accumulator
 };
+
+// ---- epilogue helpers: registers -> swizzled staging tile -> TMA store / reduce-add -----------------------------
+// A staging tile is 32 rows x 128 bytes in the SWIZZLE_128B layout the output tensor maps expect: the 16-byte chunk
+// j of row r lives at r * 128 + ((j ^ (r & 7)) << 4). Lane = row, so the eight 16-byte stores of a lane are
+// bank-conflict free, and the TMA engine turns the tile into full-line global writes (or, for the residual
+// epilogue, into fp32 reduce-adds performed by L2: the old values of C never travel to the SM).
+__device__ __forceinline__ void stage_row(uint8_t* tile, int lane, const uint32_t (&w)[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<uint4*>(tile + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_uint4(w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+// one tile of this warp: wait until the previous bulk store has read the staging tile, refill it, hand it to TMA
+__device__ __forceinline__ void emit_tile(uint8_t* tile, int lane, const uint32_t (&w)[32], const CUtensorMap* map,
+                                          int c0, int c1, bool reduce_add) {
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+  stage_row(tile, lane, w);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) {
+    if (reduce_add) tma_reduce_add_2d(map, tile, c0, c1);
+    else tma_store_2d(map, tile, c0, c1);
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  }
+}
 
 template <int ELEM_BYTES, int NTERMS, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                       float* __restrict__ C, int64_t ldc, ActOut act, int M, int N, int K, int a_plane_rows,
-                       int w_plane_rows, int epilogue, uint32_t idesc, float out_scale, int num_n_tiles,
-                       int num_tiles) {
+                       const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
+                       int* overflow, int is_fp16, int M, int N, int K, int a_plane_rows, int w_plane_rows,
+                       int epilogue, uint32_t idesc, float out_scale, int num_n_tiles, int num_tiles,
+                       unsigned long long* trace) {
   using cfg = Cfg2<ELEM_BYTES, NTERMS, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + cfg::STAGES * cfg::STAGE);
+  uint8_t* epi_smem = smem + cfg::STAGES * cfg::STAGE;              // 1024-aligned: STAGE is a multiple of 1024
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_smem + cfg::EPI_BYTES);
   uint64_t* empty_bar = full_bar + cfg::STAGES;
   uint64_t* tmem_full_bar = empty_bar + cfg::STAGES;    // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;         // [2], only the leader's copies are used
@@ -169,15 +219,18 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   const int num_kb = (K + cfg::BK - 1) / cfg::BK;
 
   if (warp == 0 && lane == 0) {
+    trace_stamp(trace, 0);
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO1) : "memory");
     for (int s = 0; s < cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tmem_full_bar[b], 1);
-      mbar_init(&tmem_empty_bar[b], 8);      // 4 epilogue warps x 2 CTAs
+      mbar_init(&tmem_empty_bar[b], 2 * kEpiWarps);      // every epilogue warp of both CTAs
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -190,31 +243,52 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
   tc_fence_before();
   cluster_sync_all();          // barriers of both CTAs initialised and TMEM allocated before any remote arrive
   tc_fence_after();
-  // everything above overlapped the tail of the previous kernel (PDL); operands are read only from here on
-  pdl_trigger();
-  pdl_wait();
+
+  // this CTA's share of one pipeline iteration `it` (tile-major, then k-block)
+  auto load_w = [&](int tile, int kb, int s) {
+    const int w0 = (tile % num_n_tiles) * BN + (int)rank * (BN / 2);      // this CTA's half of the W rows
+    uint8_t* st = smem + s * cfg::STAGE;
+#pragma unroll
+    for (int p = 0; p < cfg::PLANES; ++p)
+      tma_load_2d_2sm(&tmW, &full_bar[s], st + cfg::PLANES * cfg::A_TILE + p * cfg::W_TILE, kb * cfg::BK,
+                      w0 + p * w_plane_rows);
+  };
+  auto load_a = [&](int tile, int kb, int s) {
+    const int m0 = ((tile / num_n_tiles) * 2 + (int)rank) * BM;           // this CTA's 128 rows of the pair tile
+    uint8_t* st = smem + s * cfg::STAGE;
+#pragma unroll
+    for (int p = 0; p < cfg::PLANES; ++p)
+      tma_load_2d_2sm(&tmA, &full_bar[s], st + p * cfg::A_TILE, kb * cfg::BK, m0 + p * a_plane_rows);
+  };
+  // The weights do not depend on the previous kernel of the stream: their first pipeline stages are requested
+  // BEFORE the grid dependency resolves (PDL), so the HBM latency of the first W tiles overlaps that kernel's tail.
+  int prefetched = 0;
+  if (warp == 0 && lane == 0) {
+    const int my_tiles = (num_tiles - cluster_id + num_clusters - 1) / num_clusters;
+    const int total_it = my_tiles * num_kb;
+    prefetched = total_it < cfg::STAGES ? total_it : cfg::STAGES;
+    for (int it = 0; it < prefetched; ++it) {
+      if (leader) mbar_expect_tx(&full_bar[it], 2 * cfg::STAGE);          // both CTAs' A and W loads report here
+      load_w(cluster_id + (it / num_kb) * num_clusters, it % num_kb, it);
+    }
+  }
+  pdl_wait();                  // from here on the previous kernel's outputs (A, C) may be touched
   const uint32_t tmem_base = *tmem_base_slot;
+  if (warp == 0 && lane == 0) trace_stamp(trace, 1);
 
   if (warp == 0) {
     if (lane == 0) {
       int it = 0;
       for (int tile = cluster_id; tile < num_tiles; tile += num_clusters) {
-        const int m0 = ((tile / num_n_tiles) * 2 + (int)rank) * BM;       // this CTA's 128 rows of the pair tile
-        const int w0 = (tile % num_n_tiles) * BN + (int)rank * (BN / 2);  // this CTA's half of the W rows
         for (int kb = 0; kb < num_kb; ++kb, ++it) {
           const int s = it % cfg::STAGES;
-          const uint32_t ph = (it / cfg::STAGES) & 1;
-          mbar_wait(&empty_bar[s], ph ^ 1);
-          if (leader) mbar_expect_tx(&full_bar[s], 2 * cfg::STAGE);      // both CTAs' loads report here
-          uint8_t* st = smem + s * cfg::STAGE;
-          const int k0 = kb * cfg::BK;
-#pragma unroll
-          for (int p = 0; p < cfg::PLANES; ++p)
-            tma_load_2d_2sm(&tmA, &full_bar[s], st + p * cfg::A_TILE, k0, m0 + p * a_plane_rows);
-#pragma unroll
-          for (int p = 0; p < cfg::PLANES; ++p)
-            tma_load_2d_2sm(&tmW, &full_bar[s], st + cfg::PLANES * cfg::A_TILE + p * cfg::W_TILE, k0,
-                            w0 + p * w_plane_rows);
+          if (it >= prefetched) {
+            const uint32_t ph = (it / cfg::STAGES) & 1;
+            mbar_wait(&empty_bar[s], ph ^ 1);
+            if (leader) mbar_expect_tx(&full_bar[s], 2 * cfg::STAGE);
+            load_w(tile, kb, s);
+          }
+          load_a(tile, kb, s);
         }
       }
     }
@@ -231,6 +305,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           const uint32_t ph = (it / cfg::STAGES) & 1;
           mbar_wait(&full_bar[s], ph);
           tc_fence_after();
+          if (it == 0) trace_stamp(trace, 2);
           const uint32_t a_base = smem_u32(smem + s * cfg::STAGE);
           const uint32_t w_base = a_base + cfg::PLANES * cfg::A_TILE;
 #pragma unroll
@@ -248,73 +323,103 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         tc_commit_pair(&tmem_full_bar[buf]);
       }
+      trace_stamp(trace, 3);
     }
   } else {
-    const int q = warp & 3;
-    float* stg = reinterpret_cast<float*>(smem + cfg::STAGES * cfg::STAGE + 256) + (warp - 2) * (32 * kStgLd);
+    // ===== epilogue: warp -> (TMEM lane quarter q = warp % 4, column half ch); lane = row of the quarter =====
+    const int q = warp & 3, ch = (warp - 2) >> 2;
+    uint8_t* tile_s = epi_smem + (warp - 2) * kEpiTile;
+    constexpr int HALF = BN / 2;
+    bool bad = false;                                  // fp16 planes: a value left the representable range
     int lt = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
-    const int buf = lt & 1;
-    const int m0 = ((tile / num_n_tiles) * 2 + (int)rank) * BM;
-    const int n0 = (tile % num_n_tiles) * BN;
-    // Residual epilogue: the old values of C are an INPUT, so fetch them while the MMAs are still running
-    // (chunk 0 before waiting on the accumulator, chunk i+1 while chunk i is being transposed). Loads are issued
-    // before the stores of the previous chunk in program order: the compiler may not hoist them itself (aliasing).
-    auto load_residual = [&](int c0, float4 (&res)[8]) {
-#pragma unroll
-      for (int itr = 0; itr < 8; ++itr) {
-        const int m = m0 + q * 32 + itr * 4 + (lane >> 3), n = n0 + c0 + (lane & 7) * 4;
-        res[itr] = (m < M && n < N) ? *reinterpret_cast<const float4*>(C + (int64_t)m * ldc + n)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+      const int buf = lt & 1;
+      const int row0 = ((tile / num_n_tiles) * 2 + (int)rank) * BM + q * 32;
+      const int col0 = (tile % num_n_tiles) * BN + ch * HALF;
+      mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
+      tc_fence_after();
+      if (warp == 2 && lane == 0) {
+        if (lt == 0) trace_stamp(trace, 4);
+        // the last accumulator of this CTA is complete: only epilogues remain, let the next kernel of the stream
+        // start its prologue (PDL). Triggering earlier would park its CTAs on SMs this grid still needs.
+        if (tile + num_clusters >= num_tiles) pdl_trigger();
       }
-    };
-    float4 res[8];
-    if (epilogue == EPI_RESIDUAL) load_residual(0, res);
-    mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
-    tc_fence_after();
-    // TMEM gives each lane one ROW (32 consecutive columns). Storing that way makes every warp store touch 32
-    // different lines; transposing the 32x32 chunk through a padded per-warp shared-memory tile lets 8 lanes
-    // write 128 contiguous bytes of one row (4 rows per instruction), which cuts the LSU wavefronts 8x.
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * HALF);
+      const bool rows_live = row0 < M;                 // warp-uniform; TMA clips partially covered boxes itself
+      if (epilogue != EPI_RELU_ACT) {
+        // fp32 output: 32 columns = 128 bytes per staging row
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), r);
+        for (int c = 0; c < HALF; c += 32) {
+          uint32_t r[32];
+          tmem_ld32(taddr + (uint32_t)c, r);
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        *reinterpret_cast<float4*>(&stg[lane * kStgLd + j * 4]) =
-            make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]),
-                        __uint_as_float(r[4 * j + 3]));
-      __syncwarp();
-      float4 vals[8];
-#pragma unroll
-      for (int itr = 0; itr < 8; ++itr) {
-        float4 v = *reinterpret_cast<const float4*>(&stg[(itr * 4 + (lane >> 3)) * kStgLd + (lane & 7) * 4]);
-        v.x *= out_scale; v.y *= out_scale; v.z *= out_scale; v.w *= out_scale;
-        if (epilogue == EPI_RESIDUAL) { v.x += res[itr].x; v.y += res[itr].y; v.z += res[itr].z; v.w += res[itr].w; }
-        if (epilogue == EPI_RELU_ACT) {
-          v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * out_scale);
+          if (rows_live && col0 + c < N) emit_tile(tile_s, lane, r, &tmO0, col0 + c, row0, epilogue == EPI_RESIDUAL);
         }
-        vals[itr] = v;
-      }
-      if (epilogue == EPI_RESIDUAL && c0 + 32 < BN) load_residual(c0 + 32, res);
+      } else if (ELEM_BYTES == 4) {
+        // ReLU -> tf32 planes kept as fp32 words: 32 columns per tile, plane 0 then (x3 modes) plane 1
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 32) {
+          uint32_t r[32], hi[32];
+          tmem_ld32(taddr + (uint32_t)c, r);
 #pragma unroll
-      for (int itr = 0; itr < 8; ++itr) {
-        const int m = m0 + q * 32 + itr * 4 + (lane >> 3), n = n0 + c0 + (lane & 7) * 4;
-        if (m < M && n < N) {
-          if (epilogue == EPI_RELU_ACT) act_store4(act, (int64_t)m * N + n, vals[itr]);
-          else *reinterpret_cast<float4*>(C + (int64_t)m * ldc + n) = vals[itr];
+          for (int j = 0; j < 32; ++j) {
+            const float v = fmaxf(__uint_as_float(r[j]) * out_scale, 0.f);
+            const float h = round_tf32(v);
+            hi[j] = __float_as_uint(h);
+            r[j] = __float_as_uint(round_tf32(v - h));
+          }
+          if (rows_live && col0 + c < N) {
+            emit_tile(tile_s, lane, hi, &tmO0, col0 + c, row0, false);
+            if (NTERMS == 3) emit_tile(tile_s, lane, r, &tmO1, col0 + c, row0, false);
+          }
+        }
+      } else {
+        // ReLU -> 16-bit planes: 64 columns = 128 bytes per staging row
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 64) {
+          uint32_t r0[32], r1[32], hi[32], lo[32];
+          tmem_ld32(taddr + (uint32_t)c, r0);
+          tmem_ld32(taddr + (uint32_t)(c + 32), r1);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float a = fmaxf(__uint_as_float(j < 16 ? r0[2 * j] : r1[2 * j - 32]) * out_scale, 0.f);
+            const float b = fmaxf(__uint_as_float(j < 16 ? r0[2 * j + 1] : r1[2 * j - 31]) * out_scale, 0.f);
+            if (is_fp16) {
+              bad |= !(a <= kFp16Limit && b <= kFp16Limit);
+              const __half2 h = __floats2half2_rn(a, b);
+              const float2 hf = __half22float2(h);
+              const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+            } else {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+              const float2 hf = __bfloat1622float2(h);
+              const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+              hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+              lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+          }
+          if (rows_live && col0 + c < N) {
+            emit_tile(tile_s, lane, hi, &tmO0, col0 + c, row0, false);
+            if (NTERMS == 3) emit_tile(tile_s, lane, lo, &tmO1, col0 + c, row0, false);
+          }
         }
       }
+      // this warp is done reading the accumulator: tell the leader's MMA warp it may be overwritten
+      tc_fence_before();
       __syncwarp();
+      if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[buf]);
     }
-    // this warp is done reading the accumulator: tell the leader's MMA warp it may be overwritten
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[buf]);
-    }
+    // the staging tile must outlive the bulk store's READ of it; the global writes themselves are ordered by grid
+    // completion (the next kernel's griddepcontrol.wait / stream order), as in CUTLASS' tma_store_wait<0>()
+    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (bad && overflow) *overflow = 1;
+    if (warp == 2 && lane == 0) trace_stamp(trace, 5);
   }
   tc_fence_before();
   cluster_sync_all();          // neither CTA may free TMEM or exit while the peer can still touch it
+  if (warp == 0 && lane == 0) trace_stamp(trace, 6);
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)cfg::TMEM_COLS)
@@ -326,6 +431,7 @@ template <int ELEM_BYTES, int NTERMS, int BN>
 int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
   using cfg = Cfg2<ELEM_BYTES, NTERMS, BN>;
   static_assert(cfg::STAGES >= 2, "need at least a double-buffered pipeline");
+  static_assert(cfg::STAGE % 1024 == 0, "stages must keep the 1024-byte swizzle alignment");
   auto kern = gemm_sm100_2cta_kernel<ELEM_BYTES, NTERMS, BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -337,9 +443,21 @@ int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
   const int64_t w_plane_rows = cfg::PLANES == 2 ? g.w_plane / g.K : 0;
   const int64_t a_rows = cfg::PLANES == 2 ? a_plane_rows + g.M : g.M;
   const int64_t w_rows = cfg::PLANES == 2 ? w_plane_rows + g.N : g.N;
-  CUtensorMap tmA, tmW;
-  RB_TRY(tensor_map_2d(g.A, a_rows, g.K, BM, ELEM_BYTES, &tmA));
-  RB_TRY(tensor_map_2d(g.W, w_rows, g.K, BN / 2, ELEM_BYTES, &tmW));
+  CUtensorMap tmA, tmW, tmO0, tmO1;
+  RB_TRY(tensor_map_2d(g.A, a_rows, g.K, BM, ELEM_BYTES, &tmA, 0));
+  RB_TRY(tensor_map_2d(g.W, w_rows, g.K, BN / 2, ELEM_BYTES, &tmW, 0));
+  // output maps: boxes of 32 rows x 128 bytes, clipped by TMA at row M / column N
+  if (g.epilogue == EPI_RELU_ACT) {
+    RB_REQUIRE((g.N * ELEM_BYTES) % 16 == 0, "N=%lld: activation rows must be multiples of 16 bytes", (long long)g.N);
+    RB_TRY(tensor_map_2d(g.act.base, g.M, g.N, 32, ELEM_BYTES, &tmO0, g.N));
+    tmO1 = tmO0;
+    if (cfg::PLANES == 2)
+      RB_TRY(tensor_map_2d(static_cast<const char*>(g.act.base) + g.act.plane * ELEM_BYTES, g.M, g.N, 32, ELEM_BYTES,
+                           &tmO1, g.N));
+  } else {
+    RB_TRY(tensor_map_2d(g.C, g.M, g.N, 32, 4, &tmO0, g.ldc));
+    tmO1 = tmO0;
+  }
   const int num_n_tiles = ceil_div(g.N, BN);
   const int num_tiles = ceil_div(g.M, 2 * BM) * num_n_tiles;
   static int sm_pairs = 0;
@@ -351,9 +469,9 @@ int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
   }
   dim3 grid(2 * (num_tiles < sm_pairs ? num_tiles : sm_pairs));
   const int fmt = ELEM_BYTES == 4 ? 2 : (prec_is_fp16(g.mode) ? 0 : 1);
-  RB_CUDA(launch_pdl(kern, grid, dim3(kThreads), cfg::SMEM, s, tmA, tmW, g.C, g.ldc, g.act, (int)g.M, (int)g.N,
-                     (int)g.K, (int)a_plane_rows, (int)w_plane_rows, g.epilogue, make_idesc_pair(fmt, BN), g.out_scale,
-                     num_n_tiles, num_tiles));
+  RB_CUDA(launch_pdl(kern, grid, dim3(kThreads), cfg::SMEM, s, tmA, tmW, tmO0, tmO1, g.act.overflow,
+                     (int)prec_is_fp16(g.mode), (int)g.M, (int)g.N, (int)g.K, (int)a_plane_rows, (int)w_plane_rows,
+                     g.epilogue, make_idesc_pair(fmt, BN), g.out_scale, num_n_tiles, num_tiles, g_gemm_trace));
   launch_count()++;
   return 0;
 }

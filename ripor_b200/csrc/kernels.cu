@@ -32,31 +32,48 @@ __global__ void broadcast_row_kernel(const float* __restrict__ vec, float* __res
 // ------------------------------------------------------------------------------------------------
 // T5LayerNorm (one warp per row)
 // ------------------------------------------------------------------------------------------------
-template <bool F32OUT>
+template <bool F32OUT, int NV>   // NV float4 per lane held in registers (d <= 128 * NV); NV = 0: two-pass fallback
 __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restrict__ w, ActOut out,
                                float* __restrict__ out_f32, int64_t rows, int d, float eps, float scale) {
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
-  pdl_trigger();
   pdl_wait();
   if (row >= rows) return;
   const float4* xr = reinterpret_cast<const float4*>(x + row * d);
   const float4* wr = reinterpret_cast<const float4*>(w);
   const int d4 = d >> 2;
+  float4 v[NV > 0 ? NV : 1];
   float ss = 0.f;
-  for (int c = lane; c < d4; c += 32) {
-    const float4 v = xr[c];
-    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  if (NV > 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      v[i] = c < d4 ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);     // the row is read once and stays in registers
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) ss += v[i].x * v[i].x + v[i].y * v[i].y + v[i].z * v[i].z + v[i].w * v[i].w;
+  } else {
+    for (int c = lane; c < d4; c += 32) {
+      const float4 t = xr[c];
+      ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+    }
   }
   for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
   const float rs = 1.0f / sqrtf(ss / (float)d + eps);
-  for (int c = lane; c < d4; c += 32) {
-    const float4 v = xr[c];
-    const float4 g = wr[c];
-    float4 y = make_float4(g.x * (v.x * rs), g.y * (v.y * rs), g.z * (v.z * rs), g.w * (v.w * rs));
+  pdl_trigger();   // late: an early trigger parks the next kernel's CTAs on SMs this grid still needs
+  auto emit = [&](int c, float4 t) {
+    const float4 g = __ldg(wr + c);
+    float4 y = make_float4(g.x * (t.x * rs), g.y * (t.y * rs), g.z * (t.z * rs), g.w * (t.w * rs));
     if (scale != 1.0f) { y.x *= scale; y.y *= scale; y.z *= scale; y.w *= scale; }
     if (F32OUT) reinterpret_cast<float4*>(out_f32 + row * d)[c] = y;
     else act_store4(out, row * d + (int64_t)c * 4, y);
+  };
+  if (NV > 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i)
+      if (lane + 32 * i < d4) emit(lane + 32 * i, v[i]);
+  } else {
+    for (int c = lane; c < d4; c += 32) emit(c, xr[c]);
   }
 }
 
@@ -107,206 +124,6 @@ __device__ __forceinline__ float4 attn_core(float4 q4, int h, int c, bool active
     }
   }
   return o;
-}
-
-__global__ void self_attn_decode_kernel(SelfAttnArgs a, ActOut ctx) {
-  extern __shared__ float smem[];
-  const int inner = a.H * 64, c4n = inner >> 2;
-  const int m = blockIdx.x, c = threadIdx.x;
-  const bool active = c < c4n;
-  const int h = c >> 4;
-  const int P = a.t + 1;
-  int* anc_s = reinterpret_cast<int*>(smem);          // [L]
-  float* sc = smem + a.L;                              // [H, P]
-  const int arow = (a.rpq == 1) ? m * a.nb : m;
-  pdl_trigger();
-  pdl_wait();
-  for (int p = threadIdx.x; p < P; p += blockDim.x) anc_s[p] = a.anc[(int64_t)arow * a.L + p];
-  float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) {
-    const float4* row = reinterpret_cast<const float4*>(a.qkv + (int64_t)m * 3 * inner);
-    q4 = row[c];
-    // this position's K/V go to the cache slot (t, m); the same thread reads them back below
-    float4* ck = reinterpret_cast<float4*>(a.cache_k + ((int64_t)a.t * a.row_cap + m) * inner);
-    float4* cv = reinterpret_cast<float4*>(a.cache_v + ((int64_t)a.t * a.row_cap + m) * inner);
-    ck[c] = row[c4n + c];
-    cv[c] = row[2 * c4n + c];
-  }
-  __syncthreads();
-  const float* ck = a.cache_k;
-  const float* cv = a.cache_v;
-  const int64_t rc = a.row_cap;
-  const int t = a.t, L = a.L;
-  const float* bias = a.bias;
-  // K/V of position t were just written by this thread: read with plain loads (not the read-only path)
-  auto kp = [&](int p) { return reinterpret_cast<const float4*>(ck + ((int64_t)p * rc + anc_s[p]) * inner); };
-  auto vp = [&](int p) { return reinterpret_cast<const float4*>(cv + ((int64_t)p * rc + anc_s[p]) * inner); };
-  const int lane16 = threadIdx.x & 15;
-  // phase 1 inlined (cannot use __ldg on the freshly written slot)
-  for (int p = 0; p < P; ++p) {
-    float part = 0.f;
-    if (active) {
-      const float4 k4 = kp(p)[c];
-      part = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-    }
-    part += __shfl_xor_sync(0xffffffffu, part, 8);
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    if (active && lane16 == 0) sc[h * P + p] = part + bias[h * L + (t - p)];
-  }
-  __syncthreads();
-  {
-    const int hs = active ? h : 0;
-    float mx = -INFINITY;
-    for (int p = lane16; p < P; p += 16) mx = fmaxf(mx, sc[hs * P + p]);
-    for (int o = 8; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o, 16));
-    float sum = 0.f;
-    for (int p = lane16; p < P; p += 16) sum += expf(sc[hs * P + p] - mx);
-    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, 16);
-    __syncthreads();
-    if (active)
-      for (int p = lane16; p < P; p += 16) sc[h * P + p] = expf(sc[h * P + p] - mx) / sum;
-  }
-  __syncthreads();
-  if (active) {
-    float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int p = 0; p < P; ++p) {
-      const float pr = sc[h * P + p];
-      const float4 v4 = vp(p)[c];
-      o.x += pr * v4.x; o.y += pr * v4.y; o.z += pr * v4.z; o.w += pr * v4.w;
-    }
-    act_store4(ctx, (int64_t)m * inner + (int64_t)c * 4, o);
-  }
-}
-
-// Cross-attention for the decoder step. One CTA per (query, chunk of <= NBC beams, group of HG heads); warp = head.
-// The query's K/V rows are identical for all of its beams (the reference expands them x num_beams,
-// generation.py:231-233, we never do): a 32-position K (then V) chunk is staged ONCE in shared memory and
-// reused by every beam of the chunk. Phase 1: lane = key position, a full 64-dim dot product per (beam, position)
-// from shared memory (no shuffle reductions: the first version of this kernel spent its time issuing 4
-// shuffles + adds per 4-element partial dot). Phase 2: lane = a pair of output dims.
-constexpr int NBC = 10;          // beams per CTA
-constexpr int XHG = 4;           // heads per CTA
-constexpr int XLD = XHG * 64 + 4;  // padded row of the staged K/V chunk (floats): conflict-free 128-bit rows
-
-__global__ void __launch_bounds__(XHG * 32) cross_attn_decode_kernel(CrossAttnArgs a, ActOut ctx) {
-  extern __shared__ __align__(16) float smem[];
-  const int inner = a.H * 64;
-  const int b = blockIdx.x, hg0 = blockIdx.z * XHG;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = hg0 + warp;                      // this warp's head
-  const bool head_ok = h < a.H;
-  const int rpq = a.rows_per_query, S = a.S;
-  const int i0 = blockIdx.y * NBC;
-  const int nact = min(NBC, rpq - i0);
-  const int64_t row0 = (int64_t)b * rpq + i0;
-  float* k_s = smem;                             // [32][XLD] staged K chunk
-  float* v_s = k_s + 32 * XLD;                   // [32][XLD] staged V chunk (prefetched while phase 1 runs)
-  float* q_s = v_s + 32 * XLD;                   // [NBC][XHG*64]
-  float* sc_s = q_s + NBC * XHG * 64;            // [NBC][XHG][S]
-  pdl_trigger();
-  pdl_wait();
-  const int cols = min(XHG, a.H - hg0) * 64;     // valid floats per staged row
-  for (int e = threadIdx.x; e < NBC * XHG * 16; e += blockDim.x) {
-    const int i = e / (XHG * 16), c4 = e - i * (XHG * 16);
-    const bool ok = i < nact && c4 * 4 < cols;
-    const float* src = a.q + (row0 + (ok ? i : 0)) * inner + hg0 * 64 + (ok ? c4 * 4 : 0);
-    const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(q_s + i * XHG * 64 + c4 * 4);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d32), "l"(src), "r"(ok ? 16 : 0) : "memory");
-  }   // joins the commit group of the first K chunk below
-  const float* base = a.kv + (int64_t)b * S * a.ld + hg0 * 64;
-  const int64_t* mk = a.mask + (int64_t)b * S;
-  // 32 positions x cols floats with cp.async (16 B, zero-filled for masked / out-of-range rows): the loads of a
-  // chunk are all in flight at once instead of one L2 round trip per loop iteration
-  auto stage = [&](float* dst, int p0, int64_t off) {
-    for (int e = threadIdx.x; e < 32 * XHG * 16; e += blockDim.x) {
-      const int r = e / (XHG * 16), c4 = e - r * (XHG * 16);
-      const int p = p0 + r;
-      const bool ok = p < S && c4 * 4 < cols && mk[p < S ? p : 0] != 0;
-      const float* src = base + (int64_t)(ok ? p : 0) * a.ld + off + (ok ? c4 * 4 : 0);
-      const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst + r * XLD + c4 * 4);
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d32), "l"(src), "r"(ok ? 16 : 0) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  // ---- phase 1: scores[i][head][p] = q_i . k_p -------------------------------------------------------
-  stage(k_s, 0, a.k_off);
-  stage(v_s, 0, a.v_off);                        // V chunk 0 arrives while phase 1 computes
-  for (int p0 = 0; p0 < S; p0 += 32) {
-    if (p0 > 0) {
-      __syncthreads();
-      stage(k_s, p0, a.k_off);
-      asm volatile("cp.async.wait_group 0;" ::: "memory");
-    } else {
-      asm volatile("cp.async.wait_group 1;" ::: "memory");
-    }
-    __syncthreads();
-    float acc[NBC];
-#pragma unroll
-    for (int i = 0; i < NBC; ++i) acc[i] = 0.f;
-    const float* krow = k_s + lane * XLD + warp * 64;
-    const float* qh = q_s + warp * 64;
-#pragma unroll 4
-    for (int d4 = 0; d4 < 16; ++d4) {
-      const float4 k4 = *reinterpret_cast<const float4*>(krow + d4 * 4);
-#pragma unroll
-      for (int i = 0; i < NBC; ++i) {
-        const float4 q4 = *reinterpret_cast<const float4*>(qh + i * XHG * 64 + d4 * 4);
-        acc[i] += q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-      }
-    }
-    const int p = p0 + lane;
-    if (p < S) {
-      const bool ok = mk[p] != 0;
-#pragma unroll
-      for (int i = 0; i < NBC; ++i)
-        if (i < nact) sc_s[(i * XHG + warp) * S + p] = ok ? acc[i] : -INFINITY;
-    }
-  }
-  __syncthreads();
-  // ---- softmax over the S positions of every (beam, head) row: one warp per head -----------------------
-  for (int i = 0; i < nact; ++i) {
-    float* sc = sc_s + (i * XHG + warp) * S;
-    float m = -INFINITY;
-    for (int p = lane; p < S; p += 32) m = fmaxf(m, sc[p]);
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    float sum = 0.f;
-    for (int p = lane; p < S; p += 32) sum += expf(sc[p] - m);
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    for (int p = lane; p < S; p += 32) sc[p] = expf(sc[p] - m) / sum;
-  }
-  // ---- phase 2: out[i][head][2*lane .. +1] = sum_p prob[i][p] * v_p ------------------------------------
-  float2 o2[NBC];
-#pragma unroll
-  for (int i = 0; i < NBC; ++i) o2[i] = make_float2(0.f, 0.f);
-  for (int p0 = 0; p0 < S; p0 += 32) {
-    if (p0 > 0) {
-      __syncthreads();
-      stage(v_s, p0, a.v_off);
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-    const int np = min(32, S - p0);
-    for (int r = 0; r < np; ++r) {
-      const float2 v2 = *reinterpret_cast<const float2*>(v_s + r * XLD + warp * 64 + lane * 2);
-#pragma unroll
-      for (int i = 0; i < NBC; ++i) {
-        const float pr = (i < nact) ? sc_s[(i * XHG + warp) * S + p0 + r] : 0.f;   // masked keys: exactly 0
-        o2[i].x += pr * v2.x;
-        o2[i].y += pr * v2.y;
-      }
-    }
-  }
-  if (head_ok) {
-#pragma unroll
-    for (int i = 0; i < NBC; ++i)
-      if (i < nact) {
-        const int64_t idx = (row0 + i) * inner + h * 64 + lane * 2;
-        act_store(ctx, idx, o2[i].x);
-        act_store(ctx, idx + 1, o2[i].y);
-      }
-  }
 }
 
 __global__ void enc_attn_kernel(EncAttnArgs a, ActOut ctx) {
@@ -415,49 +232,47 @@ int launch_broadcast_row(const float* vec, float* x, int64_t rows, int d, cudaSt
   return 0;
 }
 
-int launch_rmsnorm(const float* x, const float* w, ActOut out, int64_t rows, int d, float eps, float scale,
-                   cudaStream_t s) {
+template <bool F32OUT>
+static int launch_rmsnorm_any(const float* x, const float* w, ActOut out, float* out_f32, int64_t rows, int d, float eps,
+                              float scale, cudaStream_t s) {
   if (rows == 0) return 0;
-  RB_CUDA(launch_pdl(rmsnorm_kernel<false>, dim3(ceil_div(rows, 4)), dim3(128), 0, s, x, w, out, nullptr, rows, d, eps,
-                     scale));
+  const dim3 grid(ceil_div(rows, 8)), block(256);     // one warp per row, 8 rows per CTA
+  cudaError_t err;
+  if (d <= 128 * 6) err = launch_pdl(rmsnorm_kernel<F32OUT, 6>, grid, block, 0, s, x, w, out, out_f32, rows, d, eps, scale);
+  else if (d <= 128 * 8) err = launch_pdl(rmsnorm_kernel<F32OUT, 8>, grid, block, 0, s, x, w, out, out_f32, rows, d, eps, scale);
+  else err = launch_pdl(rmsnorm_kernel<F32OUT, 0>, grid, block, 0, s, x, w, out, out_f32, rows, d, eps, scale);
+  RB_CUDA(err);
   rb::launch_count()++;
   return 0;
 }
 
+int launch_rmsnorm(const float* x, const float* w, ActOut out, int64_t rows, int d, float eps, float scale,
+                   cudaStream_t s) {
+  return launch_rmsnorm_any<false>(x, w, out, nullptr, rows, d, eps, scale, s);
+}
+
 int launch_rmsnorm_f32(const float* x, const float* w, float* out, int64_t rows, int d, float eps, cudaStream_t s) {
-  if (rows == 0) return 0;
-  rmsnorm_kernel<true><<<ceil_div(rows, 4), 128, 0, s>>>(x, w, ActOut{nullptr, 0, 0}, out, rows, d, eps, 1.0f);
-  RB_CUDA(cudaGetLastError());
-  rb::launch_count()++;
-  return 0;
+  return launch_rmsnorm_any<true>(x, w, ActOut{nullptr, 0, 0}, out, rows, d, eps, 1.0f, s);
 }
 
 static int attn_threads(int H) { return ((H * 16 + 31) / 32) * 32; }
 
+// attn_warp.cu: the decode-step attention kernels (one warp per (row, head))
+bool launch_self_attn_warp(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s, int* status);
+bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, int* status);
+
 int launch_self_attn_decode(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s) {
-  const int threads = attn_threads(a.H);
-  RB_REQUIRE(threads <= 1024, "too many heads (%d)", a.H);
-  const size_t smem = (size_t)(a.L + a.H * (a.t + 1)) * sizeof(float);
-  RB_CUDA(launch_pdl(self_attn_decode_kernel, dim3(a.M), dim3(threads), smem, s, a, ctx));
-  rb::launch_count()++;
-  return 0;
+  int st = 0;
+  launch_self_attn_warp(a, ctx, s, &st);
+  return st;
 }
 
 int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s) {
-  const int threads = XHG * 32;
-  const size_t smem = (size_t)(2 * 32 * XLD + NBC * XHG * 64 + NBC * XHG * a.S) * sizeof(float);
-  RB_REQUIRE(smem <= 200 * 1024, "S=%d too large for the cross-attention kernel", a.S);
-  static size_t smem_attr = 48 * 1024;
-  if (smem > smem_attr) {
-    RB_CUDA(cudaFuncSetAttribute(cross_attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    smem_attr = smem;
-  }
   RB_REQUIRE(a.M % a.rows_per_query == 0, "row count %d is not a multiple of rows_per_query %d", a.M,
              a.rows_per_query);
-  dim3 grid(a.M / a.rows_per_query, ceil_div(a.rows_per_query, NBC), ceil_div(a.H, XHG));
-  RB_CUDA(launch_pdl(cross_attn_decode_kernel, grid, dim3(threads), smem, s, a, ctx));
-  rb::launch_count()++;
-  return 0;
+  int st = 0;
+  launch_cross_attn_warp(a, ctx, s, &st);
+  return st;
 }
 
 int launch_enc_attn(const EncAttnArgs& a, ActOut ctx, cudaStream_t s) {

@@ -56,18 +56,21 @@ inline int64_t& launch_count() {
 }
 
 // ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
-// Every hot kernel of the engine starts with pdl_trigger() + pdl_wait(): the next kernel of the stream is
-// allowed to be scheduled (and to run its prologue: barrier init, TMEM allocation, descriptor prefetch) while
-// this one is still running, and nobody touches global memory before the previous kernel has fully completed
-// and flushed. That hides the ~2-3 us launch/scheduling gap paid ~4400 times per search.
+// Every hot kernel of the engine calls pdl_wait() before it touches global memory and pdl_trigger() once its
+// main work is done: the next kernel of the stream may then be scheduled (and run its prologue: barrier init,
+// TMEM allocation, descriptor prefetch) while this one drains, and nobody reads global memory before the previous
+// kernel has fully completed and flushed. That hides the ~3 us launch/scheduling gap paid ~4400 times per search.
+// The trigger is deliberately LATE: triggered at kernel entry, the dependent grid's CTAs (a GEMM CTA owns
+// ~200 KB of shared memory) become resident while a multi-wave grid still has CTAs to schedule and the step
+// gets slower (measured on B200: 129 ms vs 124 ms without PDL).
 #ifdef __CUDACC__
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 inline bool pdl_enabled() {
   static const bool on = []() {
-    const char* e = getenv("RB200_PDL");     // opt-in: measured gain on B200 was ~1 % (profiles/r01_summary.md)
-    return e && e[0] == '1';
+    const char* e = getenv("RB200_PDL");     // default on (+4 % on the bench step); RB200_PDL=0 disables
+    return !(e && e[0] == '0');
   }();
   return on;
 }

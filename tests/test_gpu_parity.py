@@ -267,3 +267,18 @@ def test_fp16x3_overflow_is_loud():
     w["decoder.block.0.layer.2.DenseReluDense.wi.weight"] = w["decoder.block.0.layer.2.DenseReluDense.wi.weight"] * 3e4
     with pytest.raises(ValueError, match="fp16 range"):
         _engine_search(T5SeqAQEncoder.from_weights(dims, w), trie, ids, mask, 4, dims.docid_len, precision="fp16x3")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "tf32x3"])
+@pytest.mark.parametrize("L,S,nb", [(40, 45, 12), (70, 100, 3)])
+def test_long_docid_and_source_lengths(precision, L, S, nb):
+    """More than 32 DocID positions / source tokens and more than 10 beams: the multi-chunk attention paths."""
+    dims = syn.T5Dims.tiny(docid_len=L)
+    w = syn.make_weights(dims)
+    V, B = dims.decoder_vocab_size, 3
+    codes = syn.make_codes(300, L, V)
+    ids, mask = syn.make_queries(B, S=S, vocab_size=dims.vocab_size)
+    ref_seq, ref_sc, _, _ = helpers.oracle_cached_search(w, dims, codes, ids, mask, nb, L)
+    model = T5SeqAQEncoder.from_weights(dims, w)
+    out = _engine_search(model, DocidTrie.from_codes(codes, V), ids, mask, nb, L, precision=precision)
+    assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0

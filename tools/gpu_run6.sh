@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -x -q --timeout 300 -k "golden or t5base_search or long_docid" 2>&1 | tail -4 | tee gpurun_out/pytest_gpu6.log
+timeout 300 python bench.py --steps 3 --warmup 3 --precision fp16x3 --no-cpu-baseline 2>&1 | tail -1 | tee gpurun_out/bench6_fp16x3.json | cut -c1-300
+timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches6_fp16x3.csv python tools/profile_step.py --precision fp16x3 > gpurun_out/prof6_fp16x3.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches6_fp16x3.csv | tee gpurun_out/launch_summary6_fp16x3.txt | head -9
