@@ -121,6 +121,112 @@ __global__ void __launch_bounds__(kWarps * 32, 5) self_attn_warp_kernel(SelfAttn
   }
 }
 
+// Shared-memory staged variant: ALL K/V rows of a super-chunk (up to 32 positions = 16 KB per warp) are requested
+// with cp.async before anything is computed, so a warp's whole working set is in flight at once and costs no
+// registers; the dynamic shared memory is sized from t, so early steps (few positions) run many more warps per SM.
+// Scores: lane = position (K row from shared memory, 16-byte chunks XOR-swizzled by row so the row-per-lane reads
+// are conflict free); context: lane = a pair of output dims.
+__device__ __forceinline__ void cp_async16_on(float* dst_smem, const float* src) {
+  const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src) : "memory");
+}
+
+__global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArgs a, ActOut ctx, int pcap) {
+  extern __shared__ __align__(16) float ssmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;
+  const int per_warp = pcap * 128 + 64 + 32;                        // K | V | q | exp(scores)
+  float* ks = ssmem + warp * per_warp;
+  float* vs = ks + pcap * 64;
+  float* qs = vs + pcap * 64;
+  float* es = qs + 64;
+  const int inner = a.H * 64, t = a.t, L = a.L;
+  const int ntask = a.M * a.H;
+  pdl_wait();
+  // persistent: a few resident CTAs per SM walk the (row, head) tasks (7680 four-warp CTAs cost more in block
+  // scheduling than the short early steps take to compute)
+  for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += gridDim.x * kWarps) {
+  const int m = wid / a.H, h = wid - m * a.H;
+  const int arow = (a.rpq == 1) ? m * a.nb : m;
+  const float* qrow = a.qkv + (int64_t)m * 3 * inner + h * 64;     // q | k | v of this row at position t
+  __syncwarp();                                                     // the previous task's readers are done
+  if (lane < 16) cp_async16_on(qs + lane * 4, qrow + lane * 4);
+  const float* ck = a.cache_k + h * 64 + l16 * 4;
+  const float* cv = a.cache_v + h * 64 + l16 * 4;
+  float run_max = -INFINITY, run_sum = 0.f;
+  float2 o2 = make_float2(0.f, 0.f);
+  for (int c0 = 0; c0 <= t; c0 += 32) {
+    const int np = min(32, t + 1 - c0);                             // positions of this super-chunk (warp-uniform)
+    if (c0 > 0) __syncwarp();
+    // ---- stage: lane p owns the cache slot of position c0 + p; 16 lanes x 16 B per row, 2 rows per instruction --
+    const int pl = c0 + lane;
+    const int slot_l = pl < t ? pl * (int)a.row_cap + a.anc[(int64_t)arow * L + pl] : -1;   // -1: position t (qkv)
+    const int nr = (np + 1) >> 1;
+#pragma unroll 4
+    for (int r = 0; r < nr; ++r) {
+      const int row = 2 * r + half;
+      const int slot = __shfl_sync(0xffffffffu, slot_l, row);
+      if (row < np) {
+        const float* kp = slot >= 0 ? ck + (int64_t)slot * inner : qrow + inner + l16 * 4;
+        const float* vp = slot >= 0 ? cv + (int64_t)slot * inner : qrow + 2 * inner + l16 * 4;
+        cp_async16_on(ks + row * 64 + ((l16 ^ (row & 7)) << 2), kp);
+        cp_async16_on(vs + row * 64 + l16 * 4, vp);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    const float bias = lane < np ? __ldg(a.bias + h * L + (t - pl)) : 0.f;
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    // ---- scores: lane = position ---------------------------------------------------------------------------------
+    float sc = -INFINITY;
+    if (lane < np) {
+      float acc = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j)
+        acc = dot4(*reinterpret_cast<const float4*>(qs + j * 4),
+                   *reinterpret_cast<const float4*>(ks + lane * 64 + ((j ^ (lane & 7)) << 2)), acc);
+      sc = acc + bias;
+    }
+    const float new_max = fmaxf(run_max, warp_max(sc));
+    const float rescale = expf(run_max - new_max);                  // 0 on the first chunk
+    const float e = expf(sc - new_max);                             // 0 beyond np
+    run_max = new_max;
+    run_sum = run_sum * rescale + warp_sum(e);
+    o2.x *= rescale;
+    o2.y *= rescale;
+    es[lane] = e;
+    __syncwarp();
+    // ---- context: lane = a pair of output dims; 4 positions per iteration (rows beyond np hold e = 0, and their
+    //      V rows are zero-filled below so that 0 * garbage never happens) -----------------------------------------
+    const int ng = (np + 3) >> 2;
+    for (int row = np + half; row < ng * 4; row += 2) *reinterpret_cast<float4*>(vs + row * 64 + l16 * 4) =
+        make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+#pragma unroll 2
+    for (int g = 0; g < ng; ++g) {
+      const float4 e4 = *reinterpret_cast<const float4*>(es + 4 * g);
+      const float2 v0 = *reinterpret_cast<const float2*>(vs + (4 * g + 0) * 64 + lane * 2);
+      const float2 v1 = *reinterpret_cast<const float2*>(vs + (4 * g + 1) * 64 + lane * 2);
+      const float2 v2 = *reinterpret_cast<const float2*>(vs + (4 * g + 2) * 64 + lane * 2);
+      const float2 v3 = *reinterpret_cast<const float2*>(vs + (4 * g + 3) * 64 + lane * 2);
+      o2.x = fmaf(e4.x, v0.x, o2.x); o2.y = fmaf(e4.x, v0.y, o2.y);
+      o2.x = fmaf(e4.y, v1.x, o2.x); o2.y = fmaf(e4.y, v1.y, o2.y);
+      o2.x = fmaf(e4.z, v2.x, o2.x); o2.y = fmaf(e4.z, v2.y, o2.y);
+      o2.x = fmaf(e4.w, v3.x, o2.x); o2.y = fmaf(e4.w, v3.y, o2.y);
+    }
+  }
+  // this position's K/V go to cache slot (t, m) for the later steps: 64 floats per head, one float2 per lane
+  {
+    const int64_t dst = ((int64_t)t * a.row_cap + m) * inner + h * 64 + lane * 2;
+    *reinterpret_cast<float2*>(a.cache_k + dst) = *reinterpret_cast<const float2*>(qrow + inner + lane * 2);
+    *reinterpret_cast<float2*>(a.cache_v + dst) = *reinterpret_cast<const float2*>(qrow + 2 * inner + lane * 2);
+  }
+  const float inv = 1.0f / run_sum;
+  act_store2(ctx, (int64_t)m * inner + h * 64 + lane * 2, make_float2(o2.x * inv, o2.y * inv));
+  }
+  pdl_trigger();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // cross-attention against the query's encoder K/V
 // ------------------------------------------------------------------------------------------------------------
@@ -259,7 +365,40 @@ __global__ void __launch_bounds__(kWarps * 32, QS ? 2 : 3) cross_attn_warp_kerne
 
 bool launch_self_attn_warp(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s, int* status) {
   const dim3 grid(ceil_div((int64_t)a.M * a.H, kWarps)), block(kWarps * 32);
-  const cudaError_t err = launch_pdl(self_attn_warp_kernel, grid, block, 0, s, a, ctx);
+  // Staged kernel while few positions are cached (its shared memory grows with t and the early steps are bound
+  // by per-task latency, so occupancy wins); register kernel for the long, HBM-bound steps. Measured crossover on
+  // B200 at 24 positions. RB200_SELF=smem|reg forces one of them.
+  static const int force = []() {
+    const char* e = getenv("RB200_SELF");
+    return !e ? 0 : (strcmp(e, "smem") == 0 ? 1 : (strcmp(e, "reg") == 0 ? 2 : 0));
+  }();
+  const bool staged = force == 1 || (force == 0 && a.t + 1 <= 24);
+  cudaError_t err;
+  if (staged) {
+    const int pcap = ((a.t + 1 < 32 ? a.t + 1 : 32) + 3) & ~3;      // staged positions per warp, multiple of 4
+    const size_t smem = (size_t)kWarps * (pcap * 128 + 64 + 32) * sizeof(float);
+    static bool attr_set = false;
+    static int sms = 0;
+    if (!attr_set) {
+      err = cudaFuncSetAttribute(self_attn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)kWarps * (32 * 128 + 96) * sizeof(float)));
+      int dev = 0;
+      if (err == cudaSuccess) err = cudaGetDevice(&dev);
+      if (err == cudaSuccess) err = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (err != cudaSuccess) {
+        *status = fail(RB200_ERR_CUDA, "self_attn_smem_kernel attribute: %s", cudaGetErrorString(err));
+        return true;
+      }
+      attr_set = true;
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    per_sm = per_sm > 7 ? 7 : (per_sm < 1 ? 1 : per_sm);           // 72 registers x 128 threads: 7 CTAs per SM
+    const int want = ceil_div((int64_t)a.M * a.H, kWarps);
+    const dim3 pgrid(want < sms * per_sm ? want : sms * per_sm);
+    err = launch_pdl(self_attn_smem_kernel, pgrid, block, smem, s, a, ctx, pcap);
+  } else {
+    err = launch_pdl(self_attn_warp_kernel, grid, block, 0, s, a, ctx);
+  }
   *status = err == cudaSuccess ? 0 : fail(RB200_ERR_CUDA, "self_attn_warp_kernel launch: %s", cudaGetErrorString(err));
   launch_count()++;
   return true;

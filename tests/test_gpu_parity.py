@@ -282,3 +282,30 @@ def test_long_docid_and_source_lengths(precision, L, S, nb):
     model = T5SeqAQEncoder.from_weights(dims, w)
     out = _engine_search(model, DocidTrie.from_codes(codes, V), ids, mask, nb, L, precision=precision)
     assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0
+
+
+@pytest.mark.parametrize("precision", ["tf32x3", "fp16x3"])
+@pytest.mark.parametrize("nb,V,L,n_docs,B", [(100, 256, 6, 3000, 2),      # BASELINE configs[2]: beam 100
+                                             (10, 1024, 16, 5000, 3)])    # BASELINE configs[4]: 16 x 1024 codebooks
+def test_wide_beam_and_wide_codebook_configs(precision, nb, V, L, n_docs, B):
+    dims = syn.T5Dims.tiny(docid_len=L, decoder_vocab_size=V)
+    w = syn.make_weights(dims)
+    codes = syn.make_codes(n_docs, L, V)
+    ids, mask = syn.make_queries(B, S=20, vocab_size=dims.vocab_size)
+    ref_seq, ref_sc, _, _ = helpers.oracle_cached_search(w, dims, codes, ids, mask, nb, L)
+    model = T5SeqAQEncoder.from_weights(dims, w)
+    out = _engine_search(model, DocidTrie.from_codes(codes, V), ids, mask, nb, L, precision=precision)
+    assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0
+
+
+def test_t5large_dims_match_cached_oracle():
+    """BASELINE configs[3]: t5-large (d=1024, 16 heads, d_ff=4096, 24+24 layers) at a size the CPU oracle finishes."""
+    L, nb, B, V = 4, 4, 2, 256
+    dims = syn.T5Dims.t5_large(docid_len=L)
+    w = syn.make_weights(dims)
+    codes = syn.make_codes(20000, L, V)
+    ids, mask = syn.make_queries(B, S=16)
+    ref_seq, ref_sc, _, _ = helpers.oracle_cached_search(w, dims, codes, ids, mask, nb, L)
+    model = T5SeqAQEncoder.from_weights(dims, w)
+    out = _engine_search(model, DocidTrie.from_codes(codes, V), ids, mask, nb, L, precision="fp16x3")
+    assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0
