@@ -23,7 +23,6 @@ namespace rb {
 namespace {
 
 constexpr int kWarps = 4;          // warps per CTA
-constexpr int kXB = 10;            // beams per warp in cross-attention
 
 __device__ __forceinline__ float dot4(float4 a, float4 b, float acc) {
   acc = fmaf(a.x, b.x, acc);
@@ -230,22 +229,25 @@ __global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArg
 // ------------------------------------------------------------------------------------------------------------
 // cross-attention against the query's encoder K/V
 // ------------------------------------------------------------------------------------------------------------
-constexpr int kXLd = 68;                                  // padded staged row (floats): conflict-free LDS.128 rows
-template <bool QS>                                        // QS: the beams' q rows are staged in shared memory too
-constexpr int x_warp_floats() { return 32 * kXLd + 32 * 64 + kXB * 32 + (QS ? kXB * 64 : 0); }   // K | V | exp | q
+// QS: the beams' q rows are staged in shared memory too; XB: beams (query rows) per warp. Fewer beams per warp =
+// fewer registers and less shared memory per warp, i.e. more resident warps to hide the staging latency, at the
+// price of staging a query's K/V once per group of XB beams (the repeats hit L2).
+template <bool QS, int XB>
+constexpr int x_warp_floats() { return 32 * 64 + 32 * 64 + XB * 32 + (QS ? XB * 64 : 0); }   // K | V | exp | q
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool on) {
   const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst_smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d32), "l"(src), "r"(on ? 16 : 0) : "memory");
 }
 
-template <bool QS>
-__global__ void __launch_bounds__(kWarps * 32, QS ? 2 : 3) cross_attn_warp_kernel(CrossAttnArgs a, ActOut ctx) {
+template <bool QS, int XB>
+__global__ void __launch_bounds__(kWarps * 32, XB <= 5 ? 3 : 2) cross_attn_warp_kernel(CrossAttnArgs a, ActOut ctx) {
+  constexpr int kXB = XB;
   extern __shared__ __align__(16) float xsmem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;
-  float* ks = xsmem + warp * x_warp_floats<QS>();
-  float* vs = ks + 32 * kXLd;                                      // unpadded: read as lane-contiguous float2
+  float* ks = xsmem + warp * x_warp_floats<QS, XB>();
+  float* vs = ks + 32 * 64;                                        // K rows: 16-byte chunks XOR-swizzled by row
   float* es = vs + 32 * 64;
   float* qs = es + kXB * 32;
   const int wid = blockIdx.x * kWarps + warp;
@@ -259,13 +261,14 @@ __global__ void __launch_bounds__(kWarps * 32, QS ? 2 : 3) cross_attn_warp_kerne
   const int64_t row0 = (int64_t)b * rpq + i0;
   const int64_t* mk = a.mask + (int64_t)b * S;
   // q rows of this warp's beams -> shared memory (joins the first K commit group); rows beyond nact repeat row 0
-  const float* qg = a.q + row0 * inner + h * 64;
+  const int64_t q_ld = a.q_ld ? a.q_ld : inner;
+  const float* qg = a.q + row0 * q_ld + h * 64;
   if (QS) {
     const float* qb = qg + l16 * 4;
 #pragma unroll
-    for (int r = 0; r < kXB / 2; ++r) {
+    for (int r = 0; r < (kXB + 1) / 2; ++r) {
       const int i = 2 * r + half;
-      cp_async16(qs + i * 64 + l16 * 4, qb + (int64_t)(i < nact ? i : 0) * inner, true);
+      if (i < kXB) cp_async16(qs + i * 64 + l16 * 4, qb + (int64_t)(i < nact ? i : 0) * q_ld, true);
     }
   }
   // this lane's source pointer for staging: row (half) of the chunk, 16-byte column l16; advances 2 rows per step
@@ -290,7 +293,7 @@ __global__ void __launch_bounds__(kWarps * 32, QS ? 2 : 3) cross_attn_warp_kerne
 #pragma unroll
       for (int r = 0; r < 16; ++r) {
         const bool on = (mybits >> (2 * r)) & 1u;
-        cp_async16(ks + (2 * r + half) * kXLd + l16 * 4, on ? src : a.kv, on);
+        cp_async16(ks + (2 * r + half) * 64 + ((l16 ^ ((2 * r + half) & 7)) << 2), on ? src : a.kv, on);
         src += step2;
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
@@ -311,13 +314,19 @@ __global__ void __launch_bounds__(kWarps * 32, QS ? 2 : 3) cross_attn_warp_kerne
     for (int i = 0; i < kXB; ++i) sc[i] = 0.f;
 #pragma unroll 4
     for (int j = 0; j < 16; ++j) {
-      const float4 k4 = *reinterpret_cast<const float4*>(ks + lane * kXLd + j * 4);
+      const float4 k4 = *reinterpret_cast<const float4*>(ks + lane * 64 + ((j ^ (lane & 7)) << 2));
 #pragma unroll
       for (int i = 0; i < kXB; ++i) {
         const float4 q4 = QS ? *reinterpret_cast<const float4*>(qs + i * 64 + j * 4)
-                             : __ldg(reinterpret_cast<const float4*>(qg + (int64_t)(i < nact ? i : 0) * inner) + j);
+                             : __ldg(reinterpret_cast<const float4*>(qg + (int64_t)(i < nact ? i : 0) * q_ld) + j);
         sc[i] = dot4(q4, k4, sc[i]);
       }
+    }
+    if (a.rel_bias != nullptr && ok) {   // encoder: query row i0 + i of the sequence, key p
+      const float* rb_h = a.rel_bias + (int64_t)h * (2 * S - 1) + (p + S - 1 - i0);
+#pragma unroll
+      for (int i = 0; i < kXB; ++i)
+        if (i < nact) sc[i] += __ldg(rb_h - i);
     }
 #pragma unroll
     for (int i = 0; i < kXB; ++i) {
@@ -404,25 +413,35 @@ bool launch_self_attn_warp(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s, in
   return true;
 }
 
-bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, int* status) {
+template <bool QS, int XB>
+static cudaError_t launch_cross_cfg(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s) {
   const int B = a.M / a.rows_per_query;
-  const dim3 grid(ceil_div((int64_t)B * a.H, kWarps), ceil_div(a.rows_per_query, kXB)), block(kWarps * 32);
+  const dim3 grid(ceil_div((int64_t)B * a.H, kWarps), ceil_div(a.rows_per_query, XB)), block(kWarps * 32);
+  constexpr size_t smem = (size_t)kWarps * x_warp_floats<QS, XB>() * sizeof(float);
+  auto kern = cross_attn_warp_kernel<QS, XB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  return launch_pdl(kern, grid, block, smem, s, a, ctx);
+}
+
+bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, int* status) {
   static const bool qs = []() {
     const char* e = getenv("RB200_XATTN_Q");     // default: q rows staged in shared memory (24 us vs 30 us per launch)
     return !(e && strcmp(e, "ldg") == 0);
   }();
-  const size_t smem = (size_t)kWarps * (qs ? x_warp_floats<true>() : x_warp_floats<false>()) * sizeof(float);
-  auto kern = qs ? cross_attn_warp_kernel<true> : cross_attn_warp_kernel<false>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) {
-      *status = fail(RB200_ERR_CUDA, "cross_attn_warp_kernel attribute: %s", cudaGetErrorString(e));
-      return true;
-    }
-    attr_set = true;
-  }
-  const cudaError_t err = launch_pdl(kern, grid, block, smem, s, a, ctx);
+  static const int xb_env = []() {
+    const char* e = getenv("RB200_XATTN_B");
+    return e ? atoi(e) : 0;
+  }();
+  // 5 beams per warp up to 20 rows per query (the bench shape: 10), 10 beyond (beam 100: fewer K/V restagings)
+  const int xb = xb_env ? xb_env : (a.rows_per_query <= 20 ? 5 : 10);
+  cudaError_t err;
+  if (xb == 5) err = qs ? launch_cross_cfg<true, 5>(a, ctx, s) : launch_cross_cfg<false, 5>(a, ctx, s);
+  else err = qs ? launch_cross_cfg<true, 10>(a, ctx, s) : launch_cross_cfg<false, 10>(a, ctx, s);
   *status = err == cudaSuccess ? 0 : fail(RB200_ERR_CUDA, "cross_attn_warp_kernel launch: %s", cudaGetErrorString(err));
   launch_count()++;
   return true;

@@ -48,10 +48,11 @@ struct Lane {
   void* ctx = nullptr;             // ActBuf [planes][Mcap][inner]
   void* hbuf = nullptr;            // ActBuf [planes][Mcap][dff]
   float* logits = nullptr;         // [Rcap, V]
-  float* cross_kv = nullptr;       // [BScap, Nl*2*inner]
+  float* cross_kv = nullptr;       // [Nl][BScap][2*inner]: per decoder layer, K | V of every source position
   float* enc_out = nullptr;        // [BScap, d]
   float* cache_k = nullptr;        // [Nl][Lmodel][Rcap][inner]
   float* cache_v = nullptr;
+  float* ss[2] = {nullptr, nullptr};   // NormFold: [Mcap, np] per-row partial sums of x^2, two norm points alive
   rb200_beam* beam = nullptr;
   cudaStream_t own_stream = nullptr;   // lane 1 only
   cudaEvent_t done = nullptr;
@@ -78,6 +79,11 @@ struct rb200_engine {
   int enc_bias_S = 0;
   std::set<std::string> have;
   bool finalized = false;
+  // NormFold (kernels.h): layer-norm weights folded into the packed matrices that follow them
+  struct Stash { float* src; Packed* w; int64_t row0, rows; const float* ln; float scale; };
+  bool fold = false;
+  int np = 0;
+  std::vector<Stash> stash;
   Lane lanes[2];                   // lane 0: full capacity; lane 1: the second half of a split batch
   int num_lanes = 1;
   cudaEvent_t fork = nullptr;
@@ -115,9 +121,18 @@ int alloc_packed(rb200_engine* e, Packed* w, int64_t N, int64_t K) {
 }
 
 // pack `rows` x K fp32 rows into row offset `row0` of packed weight w
-int pack_rows(rb200_engine* e, Packed* w, int64_t row0, const float* src, int64_t rows, cudaStream_t s) {
+int pack_rows(rb200_engine* e, Packed* w, int64_t row0, const float* src, int64_t rows, cudaStream_t s,
+              const float* ln = nullptr, float extra = 1.0f) {
+  if (e->fold && ln != nullptr) {
+    // the layer-norm vector may not have been set yet: keep a copy and fold when the weights are finalized
+    float* copy = nullptr;
+    RB_CUDA(cudaMalloc((void**)&copy, (size_t)rows * w->K * 4));
+    RB_CUDA(cudaMemcpyAsync(copy, src, (size_t)rows * w->K * 4, cudaMemcpyDeviceToDevice, s));
+    e->stash.push_back({copy, w, row0, rows, ln, extra});
+    return 0;
+  }
   char* dst = static_cast<char*>(w->ptr) + row0 * w->K * e->elem;
-  const float scale = rb::prec_is_fp16(e->mode) ? rb::kFp16WeightScale : 1.0f;
+  const float scale = rb::prec_is_fp16(e->mode) ? rb::kFp16WeightScale : 1.0f;   // (extra only applies when folding)
   return rb::launch_pack_planes(src, dst, rows * w->K, w->plane, e->mode, scale, e->overflow + 1, s);
 }
 
@@ -127,8 +142,9 @@ int copy_f32(float* dst, const float* src, int64_t n, cudaStream_t s) {
 }
 
 int gemm(rb200_engine* e, const Lane& l, const void* A, int64_t a_row_len, const Packed& w, float* C, int64_t ldc,
-         ActOut act, int64_t M, int epi, cudaStream_t s) {
+         ActOut act, int64_t M, int epi, cudaStream_t s, rb::NormFold nf = rb::NormFold{}) {
   GemmArgs g;
+  g.nf = nf;
   g.mode = e->mode;
   g.A = A; g.a_plane = l.Mcap * a_row_len;
   g.W = w.ptr; g.w_plane = w.plane;
@@ -148,6 +164,14 @@ int gemm(rb200_engine* e, const Lane& l, const void* A, int64_t a_row_len, const
   e->ev_used += 2;
   e->prof_flops += 2.0 * (double)M * (double)w.N * (double)w.K;
   return st;
+}
+
+// rows [row0, row0 + rows) of a packed weight as a weight of its own (same planes, same plane distance)
+Packed sub_rows(const rb200_engine* e, const Packed& w, int64_t row0, int64_t rows) {
+  Packed p = w;
+  p.ptr = static_cast<char*>(w.ptr) + row0 * w.K * e->elem;
+  p.N = rows;
+  return p;
 }
 
 // fp16x3: an activation left the fp16 range somewhere in this search -> make the result unmistakably invalid
@@ -254,6 +278,15 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
   RB_TRY(dev_alloc(e, (void**)&e->start_emb, d * 4));
   RB_TRY(dev_alloc(e, (void**)&e->enc_final_ln, d * 4));
   RB_TRY(dev_alloc(e, (void**)&e->dec_final_ln, d * 4));
+  {
+    const char* f = getenv("RB200_FOLD");
+    const char* gk = getenv("RB200_GEMM");
+    // Opt-in (RB200_FOLD=1): parity-green on B200, but the row-per-lane reads/writes of the old residual values in
+    // the EPI_RESID_NORM epilogue cost as much as the 36 RMSNorm launches they replace (2550 vs 2610 q/s at the
+    // bench shape); it needs a second staging tile per epilogue warp (TMA loads of C) to pay off.
+    e->fold = e->mode != RB200_PREC_FP32 && d % 64 == 0 && (f && f[0] == '1') && !(gk && strcmp(gk, "1cta") == 0);
+    e->np = d / 64;
+  }
   // workspaces: lane 0 can hold a whole batch, lane 1 the second half of a split one
   const int64_t pe = (int64_t)e->planes * e->elem;
   {
@@ -280,6 +313,7 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
     const int64_t cache = (int64_t)cfg->num_decoder_layers * e->Lmodel * l.Rcap * inner * 4;
     RB_TRY(dev_alloc(e, (void**)&l.cache_k, cache));
     RB_TRY(dev_alloc(e, (void**)&l.cache_v, cache));
+    for (int b = 0; b < 2; ++b) RB_TRY(dev_alloc(e, (void**)&l.ss[b], l.Mcap * std::max(e->np, 1) * 4));
     // planes of the activation buffers may be read past M by TMA boxes: start from defined contents
     RB_CUDA(cudaMemset(l.xn, 0, (size_t)(l.Mcap * d * pe)));
     RB_CUDA(cudaMemset(l.ctx, 0, (size_t)(l.Mcap * inner * pe)));
@@ -316,13 +350,15 @@ int rb200_engine_free(rb200_engine* e) {
                   e->ids_dev, e->mask_dev, e->seq_dev, e->score_dev, e->leaf_dev, e->overflow};
   for (void* b : bufs) cudaFree(b);
   for (Lane& l : e->lanes) {
-    void* lb[] = {l.x, l.xn, l.qkv, l.q2, l.ctx, l.hbuf, l.logits, l.cross_kv, l.enc_out, l.cache_k, l.cache_v};
+    void* lb[] = {l.x, l.xn, l.qkv, l.q2, l.ctx, l.hbuf, l.logits, l.cross_kv, l.enc_out, l.cache_k, l.cache_v,
+                  l.ss[0], l.ss[1]};
     for (void* b : lb) cudaFree(b);
     rb200_beam_free(l.beam);
     if (l.done) cudaEventDestroy(l.done);
     if (l.own_stream) cudaStreamDestroy(l.own_stream);
   }
   if (e->fork) cudaEventDestroy(e->fork);
+  for (auto& st : e->stash) cudaFree(st.src);
   for (auto ev : e->events) cudaEventDestroy(ev);
   delete e;
   return 0;
@@ -343,6 +379,7 @@ int rb200_engine_set_weight(rb200_engine* e, const char* name_c, const float* da
   int layer = -1, sub = -1, pos = -1;
   char what[64] = {0};
   int st = 0;
+  const float out_scale_fold = e->cfg.scaleup_output_hidden ? 1.0f / sqrtf((float)d) : 1.0f;
   if (name == "shared.weight" || name == "encoder.embed_tokens.weight") {
     RB_TRY(expect((int64_t)e->cfg.vocab_size * d));
     st = copy_f32(e->shared_emb, data, numel, s);
@@ -361,11 +398,13 @@ int rb200_engine_set_weight(rb200_engine* e, const char* name_c, const float* da
     RB_REQUIRE(pos >= 0 && pos < e->Lmodel, "%s: position outside [0, %d)", name_c, e->Lmodel);
     RB_TRY(expect(V * d));
     RB_TRY(copy_f32(e->in_tab[pos], data, numel, s));
-    if (e->cfg.shared_output_input_embeds) st = pack_rows(e, &e->out_tab[pos], 0, data, V, s);
+    if (e->cfg.shared_output_input_embeds)
+      st = pack_rows(e, &e->out_tab[pos], 0, data, V, s, e->dec_final_ln, out_scale_fold);
   } else if (sscanf(name_c, "list_output_embeds.%d.weight", &pos) == 1) {
     RB_REQUIRE(pos >= 0 && pos < e->Lmodel, "%s: position outside [0, %d)", name_c, e->Lmodel);
     RB_TRY(expect(V * d));
-    if (!e->cfg.shared_output_input_embeds) st = pack_rows(e, &e->out_tab[pos], 0, data, V, s);
+    if (!e->cfg.shared_output_input_embeds)
+      st = pack_rows(e, &e->out_tab[pos], 0, data, V, s, e->dec_final_ln, out_scale_fold);
   } else if (sscanf(name_c, "encoder.block.%d.layer.%d.%63s", &layer, &sub, what) == 3 ||
              sscanf(name_c, "decoder.block.%d.layer.%d.%63s", &layer, &sub, what) == 3) {
     const bool is_dec = name.compare(0, 7, "decoder") == 0;
@@ -390,23 +429,23 @@ int rb200_engine_set_weight(rb200_engine* e, const char* name_c, const float* da
                             w == "SelfAttention.v.weight")) {
       RB_TRY(expect(inner * d));
       const int which = w[14] == 'q' ? 0 : (w[14] == 'k' ? 1 : 2);
-      st = pack_rows(e, &l.qkv, which * inner, data, inner, s);
+      st = pack_rows(e, &l.qkv, which * inner, data, inner, s, l.ln0);
     } else if (sub == 0 && w == "SelfAttention.o.weight") {
       RB_TRY(expect(d * inner));
       st = pack_rows(e, &l.o, 0, data, d, s);
     } else if (is_dec && sub == 1 && w == "EncDecAttention.q.weight") {
       RB_TRY(expect(inner * d));
-      st = pack_rows(e, &l.cq, 0, data, inner, s);
+      st = pack_rows(e, &l.cq, 0, data, inner, s, l.ln1);
     } else if (is_dec && sub == 1 && (w == "EncDecAttention.k.weight" || w == "EncDecAttention.v.weight")) {
       RB_TRY(expect(inner * d));
       const int which = w[16] == 'k' ? 0 : 1;
-      st = pack_rows(e, &e->ckv, ((int64_t)layer * 2 + which) * inner, data, inner, s);
+      st = pack_rows(e, &e->ckv, ((int64_t)layer * 2 + which) * inner, data, inner, s, e->enc_final_ln);
     } else if (is_dec && sub == 1 && w == "EncDecAttention.o.weight") {
       RB_TRY(expect(d * inner));
       st = pack_rows(e, &l.co, 0, data, d, s);
     } else if (sub == ff_sub && w == "DenseReluDense.wi.weight") {
       RB_TRY(expect(dff * d));
-      st = pack_rows(e, &l.wi, 0, data, dff, s);
+      st = pack_rows(e, &l.wi, 0, data, dff, s, is_dec ? l.ln2 : l.ln1);
     } else if (sub == ff_sub && w == "DenseReluDense.wo.weight") {
       RB_TRY(expect(d * dff));
       st = pack_rows(e, &l.wo, 0, data, d, s);
@@ -450,8 +489,17 @@ int rb200_engine_finalize_weights(rb200_engine* e, void* stream) {
   }
   for (const auto& n : need)
     if (!e->have.count(n)) return rb::fail(RB200_ERR_STATE, "weight %s has not been set", n.c_str());
+  // NormFold: every layer-norm vector is on the device now - pack W * diag(ln) for the matrices that follow one
+  for (auto& st : e->stash) {
+    char* dst = static_cast<char*>(st.w->ptr) + st.row0 * st.w->K * e->elem;
+    const float scale = (rb::prec_is_fp16(e->mode) ? rb::kFp16WeightScale : 1.0f) * st.scale;
+    RB_TRY(rb::launch_pack_planes_cols(st.src, dst, st.rows * st.w->K, st.w->plane, e->mode, scale, st.ln, st.w->K,
+                                       e->overflow + 1, (cudaStream_t)stream));
+  }
   RB_TRY(build_bias_tables(e, 0, (cudaStream_t)stream));
   RB_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+  for (auto& st : e->stash) cudaFree(st.src);
+  e->stash.clear();
   int wflag = 0;
   RB_CUDA(cudaMemcpy(&wflag, e->overflow + 1, 4, cudaMemcpyDeviceToHost));
   if (wflag)
@@ -471,11 +519,47 @@ int lane_encode(rb200_engine* e, Lane& l, const int64_t* ids, const int64_t* mas
   const int d = e->d, inner = e->inner, dff = e->dff;
   const float eps = e->cfg.layer_norm_eps;
   RB_TRY(rb::launch_embed_rows(e->shared_emb, ids, l.x, rows, d, s));
+  // bidirectional self-attention = the decode cross-attention kernel with the S rows of a sequence as its "beams",
+  // K/V taken from the fused q|k|v rows, plus the relative position bias
+  auto enc_attn = [&]() {
+    rb::CrossAttnArgs ca;
+    ca.q = l.qkv; ca.q_ld = 3 * inner; ca.kv = l.qkv; ca.ld = 3 * inner; ca.k_off = inner; ca.v_off = 2 * inner;
+    ca.mask = mask; ca.M = (int)rows; ca.H = e->H; ca.S = S; ca.rows_per_query = S; ca.rel_bias = e->enc_bias;
+    return rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s);
+  };
+  if (e->fold) {
+    // NormFold chain: p = parity of the partial-sum table that holds the CURRENT norm point
+    int p = 0;
+    auto consumer = [&]() {
+      rb::NormFold nf;
+      nf.ss_prev = l.ss[p ^ 1]; nf.ss_cur = l.ss[p]; nf.np = e->np; nf.inv_d = 1.0f / (float)d; nf.eps = eps;
+      nf.scaled = true;
+      return nf;
+    };
+    auto producer = [&]() {
+      rb::NormFold nf;
+      nf.ss_prev = l.ss[p]; nf.ss_out = l.ss[p ^ 1]; nf.np = e->np; nf.inv_d = 1.0f / (float)d; nf.eps = eps;
+      p ^= 1;
+      return nf;
+    };
+    RB_TRY(rb::launch_norm_init(l.x, e->act(l, l.xn, d), l.ss[0], l.ss[1], e->np, rows, d, eps, s));
+    for (auto& w : e->enc) {
+      RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, rows, rb::EPI_STORE, s, consumer()));
+      RB_TRY(enc_attn());
+      RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, e->act(l, l.xn, d), rows, rb::EPI_RESID_NORM, s, producer()));
+      RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), rows, rb::EPI_RELU_ACT, s, consumer()));
+      RB_TRY(gemm(e, l, l.hbuf, dff, w.wo, l.x, d, e->act(l, l.xn, d), rows, rb::EPI_RESID_NORM, s, producer()));
+    }
+    RB_TRY(rb::launch_rmsnorm_f32(l.x, e->enc_final_ln, l.enc_out, rows, d, eps, s));
+    for (size_t i = 0; i < e->dec.size(); ++i)
+      RB_TRY(gemm(e, l, l.xn, d, sub_rows(e, e->ckv, (int64_t)i * 2 * inner, 2 * inner),
+                  l.cross_kv + (int64_t)i * l.BScap * 2 * inner, 2 * inner, ActOut{}, rows, rb::EPI_STORE, s, consumer()));
+    return 0;
+  }
   for (auto& w : e->enc) {
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln0, e->act(l, l.xn, d), rows, d, eps, 1.0f, s));
     RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, rows, rb::EPI_STORE, s));
-    rb::EncAttnArgs ea{l.qkv, mask, e->enc_bias, batch, S, e->H};
-    RB_TRY(rb::launch_enc_attn(ea, e->act(l, l.ctx, inner), s));
+    RB_TRY(enc_attn());
     RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, rows, rb::EPI_RESIDUAL, s));
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), rows, d, eps, 1.0f, s));
     RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), rows, rb::EPI_RELU_ACT, s));
@@ -483,8 +567,12 @@ int lane_encode(rb200_engine* e, Lane& l, const int64_t* ids, const int64_t* mas
   }
   RB_TRY(rb::launch_rmsnorm_f32(l.x, e->enc_final_ln, l.enc_out, rows, d, eps, s));
   RB_TRY(rb::launch_rmsnorm(l.x, e->enc_final_ln, e->act(l, l.xn, d), rows, d, eps, 1.0f, s));
-  // cross-attention K/V of every decoder layer in one GEMM: [B*S, d] x [d, Nl*2*inner]
-  RB_TRY(gemm(e, l, l.xn, d, e->ckv, l.cross_kv, e->ckv.N, ActOut{}, rows, rb::EPI_STORE, s));
+  // cross-attention K/V of every decoder layer, one GEMM per layer into a layer-major table [Nl][B*S][K | V]: the
+  // rows a decode-step cross-attention launch reads are then one dense 6 KB-per-position block per query instead of
+  // 3 KB pieces 74 KB apart (DRAM page locality)
+  for (size_t i = 0; i < e->dec.size(); ++i)
+    RB_TRY(gemm(e, l, l.xn, d, sub_rows(e, e->ckv, (int64_t)i * 2 * inner, 2 * inner),
+                l.cross_kv + (int64_t)i * l.BScap * 2 * inner, 2 * inner, ActOut{}, rows, rb::EPI_STORE, s));
   return 0;
 }
 
@@ -497,24 +585,59 @@ int lane_decode_step(rb200_engine* e, Lane& l, const rb200_beam* beam, int t, fl
     RB_TRY(rb::launch_broadcast_row(e->start_emb, l.x, M, d, s));
   }
   const int64_t layer_cache = (int64_t)e->Lmodel * l.Rcap * inner;
-  const int64_t ckv_ld = e->ckv.N;
-  for (size_t i = 0; i < e->dec.size(); ++i) {
-    Layer& w = e->dec[i];
-    RB_TRY(rb::launch_rmsnorm(l.x, w.ln0, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
+  auto self_attn = [&](size_t i) {
     rb::SelfAttnArgs sa;
     sa.qkv = l.qkv; sa.cache_k = l.cache_k + i * layer_cache; sa.cache_v = l.cache_v + i * layer_cache;
     sa.anc = beam->anc[beam->cur]; sa.bias = e->dec_bias; sa.row_cap = l.Rcap;
     sa.M = (int)M; sa.H = e->H; sa.L = e->Lmodel; sa.t = t; sa.rpq = rpq; sa.nb = l.nb;
-    RB_TRY(rb::launch_self_attn_decode(sa, e->act(l, l.ctx, inner), s));
+    return rb::launch_self_attn_decode(sa, e->act(l, l.ctx, inner), s);
+  };
+  auto cross_attn = [&](size_t i) {
+    rb::CrossAttnArgs ca;
+    ca.q = l.q2; ca.kv = l.cross_kv + (int64_t)i * l.BScap * 2 * inner; ca.ld = 2 * inner; ca.k_off = 0;
+    ca.v_off = inner; ca.mask = l.cur_mask; ca.M = (int)M; ca.H = e->H; ca.S = l.S;
+    ca.rows_per_query = rpq;
+    return rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s);
+  };
+  if (e->fold) {
+    int p = 0;   // parity of the partial-sum table holding the current norm point (see lane_encode)
+    auto consumer = [&]() {
+      rb::NormFold nf;
+      nf.ss_prev = l.ss[p ^ 1]; nf.ss_cur = l.ss[p]; nf.np = e->np; nf.inv_d = 1.0f / (float)d; nf.eps = eps;
+      nf.scaled = true;
+      return nf;
+    };
+    auto producer = [&]() {
+      rb::NormFold nf;
+      nf.ss_prev = l.ss[p]; nf.ss_out = l.ss[p ^ 1]; nf.np = e->np; nf.inv_d = 1.0f / (float)d; nf.eps = eps;
+      p ^= 1;
+      return nf;
+    };
+    RB_TRY(rb::launch_norm_init(l.x, e->act(l, l.xn, d), l.ss[0], l.ss[1], e->np, M, d, eps, s));
+    for (size_t i = 0; i < e->dec.size(); ++i) {
+      Layer& w = e->dec[i];
+      RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s, consumer()));
+      RB_TRY(self_attn(i));
+      RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, e->act(l, l.xn, d), M, rb::EPI_RESID_NORM, s, producer()));
+      RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s, consumer()));
+      RB_TRY(cross_attn(i));
+      RB_TRY(gemm(e, l, l.ctx, inner, w.co, l.x, d, e->act(l, l.xn, d), M, rb::EPI_RESID_NORM, s, producer()));
+      RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), M, rb::EPI_RELU_ACT, s, consumer()));
+      RB_TRY(gemm(e, l, l.hbuf, dff, w.wo, l.x, d, e->act(l, l.xn, d), M, rb::EPI_RESID_NORM, s, producer()));
+    }
+    // final layer norm (and the optional d^-1/2) live in the packed output tables
+    RB_TRY(gemm(e, l, l.xn, d, e->out_tab[t], logits, e->V, ActOut{}, M, rb::EPI_STORE, s, consumer()));
+    return 0;
+  }
+  for (size_t i = 0; i < e->dec.size(); ++i) {
+    Layer& w = e->dec[i];
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln0, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
+    RB_TRY(self_attn(i));
     RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
     RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
-    rb::CrossAttnArgs ca;
-    ca.q = l.q2; ca.kv = l.cross_kv; ca.ld = ckv_ld; ca.k_off = (int64_t)(i * 2) * inner;
-    ca.v_off = (int64_t)(i * 2 + 1) * inner; ca.mask = l.cur_mask; ca.M = (int)M; ca.H = e->H; ca.S = l.S;
-    ca.rows_per_query = rpq;
-    RB_TRY(rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s));
+    RB_TRY(cross_attn(i));
     RB_TRY(gemm(e, l, l.ctx, inner, w.co, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln2, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
     RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), M, rb::EPI_RELU_ACT, s));

@@ -375,6 +375,7 @@ int launch_gemm_sm100(const GemmArgs& g, cudaStream_t s) {
     return !(e && strcmp(e, "1cta") == 0);
   }();
   if (use_pair) return launch_gemm_sm100_2cta(g, s);
+  RB_REQUIRE(g.epilogue != EPI_RESID_NORM && !g.nf.scaled, "the 1-CTA GEMM has no NormFold epilogues");
   const int elem = prec_elem_bytes(g.mode);
   RB_REQUIRE(g.K % (16 / elem) == 0, "K=%lld must be a multiple of %d for TMA", (long long)g.K, 16 / elem);
   RB_REQUIRE(g.N % 4 == 0, "N=%lld must be a multiple of 4", (long long)g.N);

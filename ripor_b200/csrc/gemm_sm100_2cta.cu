@@ -199,9 +199,10 @@ template <int ELEM_BYTES, int NTERMS, int BN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
 gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                        const __grid_constant__ CUtensorMap tmO0, const __grid_constant__ CUtensorMap tmO1,
-                       int* overflow, int is_fp16, int M, int N, int K, int a_plane_rows, int w_plane_rows,
-                       int epilogue, uint32_t idesc, float out_scale, int num_n_tiles, int num_tiles,
-                       unsigned long long* trace) {
+                       const __grid_constant__ CUtensorMap tmO2, const float* __restrict__ Cin, int64_t ldc,
+                       NormFold nf, int* overflow, int is_fp16, int M, int N, int K, int a_plane_rows,
+                       int w_plane_rows, int epilogue, uint32_t idesc, float out_scale, int num_n_tiles,
+                       int num_tiles, unsigned long long* trace) {
   using cfg = Cfg2<ELEM_BYTES, NTERMS, BN>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -224,6 +225,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO1) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmO2) : "memory");
     for (int s = 0; s < cfg::STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -336,6 +338,34 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       const int buf = lt & 1;
       const int row0 = ((tile / num_n_tiles) * 2 + (int)rank) * BM + q * 32;
       const int col0 = (tile % num_n_tiles) * BN + ch * HALF;
+      // ---- everything that does not need the accumulator happens while the MMAs are still running ----
+      // NormFold: r^2 = mean(x^2) + eps from the per-row partial sums (lane = row)
+      const int myrow = row0 + lane;
+      float rowscale = out_scale, inv_ref = 1.0f;
+      if (nf.ss_prev != nullptr) {
+        float sp = 0.f, sc = 0.f;
+        if (myrow < M) {
+          for (int i = 0; i < nf.np; ++i) sp += nf.ss_prev[(int64_t)myrow * nf.np + i];
+          if (nf.scaled)
+            for (int i = 0; i < nf.np; ++i) sc += nf.ss_cur[(int64_t)myrow * nf.np + i];
+        }
+        const float r2_prev = fmaf(sp, nf.inv_d, nf.eps);
+        inv_ref = 1.0f / sqrtf(r2_prev);
+        if (nf.scaled) rowscale = out_scale * sqrtf(r2_prev / fmaf(sc, nf.inv_d, nf.eps));
+      }
+      // EPI_RESID_NORM: the old values of this lane's row for the first 64 columns (row-per-lane 128-byte reads)
+      const float* xrow = Cin + (int64_t)(myrow < M ? myrow : 0) * ldc;
+      auto load_x = [&](int cb, float4 (&xo)[8]) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          xo[j] = (myrow < M && cb + 4 * j < N) ? *reinterpret_cast<const float4*>(xrow + cb + 4 * j)
+                                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+      };
+      float4 xo[2][8];
+      if (epilogue == EPI_RESID_NORM) {
+        load_x(col0, xo[0]);
+        load_x(col0 + 32, xo[1]);
+      }
       mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
       tc_fence_after();
       if (warp == 2 && lane == 0) {
@@ -346,14 +376,89 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
       }
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + ch * HALF);
       const bool rows_live = row0 < M;                 // warp-uniform; TMA clips partially covered boxes itself
-      if (epilogue != EPI_RELU_ACT) {
+      if (epilogue == EPI_RESID_NORM) {
+        // C = C + acc; planes(C / r_prev) for the consuming GEMM; per-row partial sums of C^2 (NormFold)
+#pragma unroll 1
+        for (int c = 0; c < HALF; c += 64) {
+          uint32_t xn[2][32];
+          float ssq = 0.f;
+          if (c > 0) {
+            load_x(col0 + c, xo[0]);
+            load_x(col0 + c + 32, xo[1]);
+          }
+#pragma unroll
+          for (int hc = 0; hc < 2; ++hc) {
+            uint32_t r[32];
+            tmem_ld32(taddr + (uint32_t)(c + hc * 32), r);
+            float* xdst = const_cast<float*>(xrow) + col0 + c + hc * 32;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float v0 = fmaf(__uint_as_float(r[4 * j + 0]), out_scale, xo[hc][j].x);
+              const float v1 = fmaf(__uint_as_float(r[4 * j + 1]), out_scale, xo[hc][j].y);
+              const float v2 = fmaf(__uint_as_float(r[4 * j + 2]), out_scale, xo[hc][j].z);
+              const float v3 = fmaf(__uint_as_float(r[4 * j + 3]), out_scale, xo[hc][j].w);
+              ssq += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
+              xn[hc][4 * j + 0] = __float_as_uint(v0); xn[hc][4 * j + 1] = __float_as_uint(v1);
+              xn[hc][4 * j + 2] = __float_as_uint(v2); xn[hc][4 * j + 3] = __float_as_uint(v3);
+              // the new residual row goes straight back from registers (fire-and-forget 16-byte stores; L2 merges
+              // them), which keeps the single staging tile free for the two plane tiles below
+              if (myrow < M && col0 + c + hc * 32 + 4 * j < N)
+                *reinterpret_cast<float4*>(xdst + 4 * j) = make_float4(v0, v1, v2, v3);
+            }
+          }
+          if (myrow < M && col0 + c < N) nf.ss_out[(int64_t)myrow * nf.np + ((col0 + c) >> 6)] = ssq;
+          // operand planes of x / r_prev for the next GEMM
+          if (ELEM_BYTES == 4) {
+#pragma unroll
+            for (int hc = 0; hc < 2; ++hc) {
+              uint32_t hi[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float v = __uint_as_float(xn[hc][j]) * inv_ref;
+                const float h = round_tf32(v);
+                hi[j] = __float_as_uint(h);
+                xn[hc][j] = __float_as_uint(round_tf32(v - h));
+              }
+              if (rows_live && col0 + c + hc * 32 < N) {
+                emit_tile(tile_s, lane, hi, &tmO1, col0 + c + hc * 32, row0, false);
+                if (NTERMS == 3) emit_tile(tile_s, lane, xn[hc], &tmO2, col0 + c + hc * 32, row0, false);
+              }
+            }
+          } else {
+            uint32_t hi[32], lo[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float a = __uint_as_float(j < 16 ? xn[0][2 * j] : xn[1][2 * j - 32]) * inv_ref;
+              const float b = __uint_as_float(j < 16 ? xn[0][2 * j + 1] : xn[1][2 * j - 31]) * inv_ref;
+              if (is_fp16) {
+                bad |= !(fabsf(a) <= kFp16Limit && fabsf(b) <= kFp16Limit);
+                const __half2 h = __floats2half2_rn(a, b);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+                hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+              } else {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+                const float2 hf = __bfloat1622float2(h);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(a - hf.x, b - hf.y);
+                hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+                lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+              }
+            }
+            if (rows_live && col0 + c < N) {
+              emit_tile(tile_s, lane, hi, &tmO1, col0 + c, row0, false);
+              if (NTERMS == 3) emit_tile(tile_s, lane, lo, &tmO2, col0 + c, row0, false);
+            }
+          }
+        }
+      } else if (epilogue != EPI_RELU_ACT) {
         // fp32 output: 32 columns = 128 bytes per staging row
 #pragma unroll 1
         for (int c = 0; c < HALF; c += 32) {
           uint32_t r[32];
           tmem_ld32(taddr + (uint32_t)c, r);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * out_scale);
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * rowscale);
           if (rows_live && col0 + c < N) emit_tile(tile_s, lane, r, &tmO0, col0 + c, row0, epilogue == EPI_RESIDUAL);
         }
       } else if (ELEM_BYTES == 4) {
@@ -364,7 +469,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tmem_ld32(taddr + (uint32_t)c, r);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float v = fmaxf(__uint_as_float(r[j]) * out_scale, 0.f);
+            const float v = fmaxf(__uint_as_float(r[j]) * rowscale, 0.f);
             const float h = round_tf32(v);
             hi[j] = __float_as_uint(h);
             r[j] = __float_as_uint(round_tf32(v - h));
@@ -383,8 +488,8 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tmem_ld32(taddr + (uint32_t)(c + 32), r1);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float a = fmaxf(__uint_as_float(j < 16 ? r0[2 * j] : r1[2 * j - 32]) * out_scale, 0.f);
-            const float b = fmaxf(__uint_as_float(j < 16 ? r0[2 * j + 1] : r1[2 * j - 31]) * out_scale, 0.f);
+            const float a = fmaxf(__uint_as_float(j < 16 ? r0[2 * j] : r1[2 * j - 32]) * rowscale, 0.f);
+            const float b = fmaxf(__uint_as_float(j < 16 ? r0[2 * j + 1] : r1[2 * j - 31]) * rowscale, 0.f);
             if (is_fp16) {
               bad |= !(a <= kFp16Limit && b <= kFp16Limit);
               const __half2 h = __floats2half2_rn(a, b);
@@ -443,20 +548,34 @@ int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
   const int64_t w_plane_rows = cfg::PLANES == 2 ? g.w_plane / g.K : 0;
   const int64_t a_rows = cfg::PLANES == 2 ? a_plane_rows + g.M : g.M;
   const int64_t w_rows = cfg::PLANES == 2 ? w_plane_rows + g.N : g.N;
-  CUtensorMap tmA, tmW, tmO0, tmO1;
+  CUtensorMap tmA, tmW, tmO0, tmO1, tmO2;
   RB_TRY(tensor_map_2d(g.A, a_rows, g.K, BM, ELEM_BYTES, &tmA, 0));
   RB_TRY(tensor_map_2d(g.W, w_rows, g.K, BN / 2, ELEM_BYTES, &tmW, 0));
-  // output maps: boxes of 32 rows x 128 bytes, clipped by TMA at row M / column N
-  if (g.epilogue == EPI_RELU_ACT) {
+  // output maps: boxes of 32 rows x 128 bytes, clipped by TMA at row M / column N.
+  //   EPI_STORE / EPI_RESIDUAL: O0 = C            EPI_RELU_ACT: O0, O1 = activation planes
+  //   EPI_RESID_NORM: O0 = C, O1, O2 = activation planes
+  const bool planes_out = g.epilogue == EPI_RELU_ACT || g.epilogue == EPI_RESID_NORM;
+  if (planes_out) {
     RB_REQUIRE((g.N * ELEM_BYTES) % 16 == 0, "N=%lld: activation rows must be multiples of 16 bytes", (long long)g.N);
-    RB_TRY(tensor_map_2d(g.act.base, g.M, g.N, 32, ELEM_BYTES, &tmO0, g.N));
-    tmO1 = tmO0;
+    RB_REQUIRE(g.act.base != nullptr, "this epilogue needs an activation output buffer");
+  }
+  if (g.epilogue == EPI_RESID_NORM) {
+    RB_REQUIRE(g.N % 64 == 0 && g.nf.ss_prev && g.nf.ss_out && g.nf.np == g.N / 64,
+               "EPI_RESID_NORM needs N %% 64 == 0 and the NormFold tables (np = N / 64)");
+  }
+  if (g.epilogue != EPI_RELU_ACT) RB_TRY(tensor_map_2d(g.C, g.M, g.N, 32, 4, &tmO0, g.ldc));
+  if (planes_out) {
+    CUtensorMap p0, p1;
+    RB_TRY(tensor_map_2d(g.act.base, g.M, g.N, 32, ELEM_BYTES, &p0, g.N));
+    p1 = p0;
     if (cfg::PLANES == 2)
       RB_TRY(tensor_map_2d(static_cast<const char*>(g.act.base) + g.act.plane * ELEM_BYTES, g.M, g.N, 32, ELEM_BYTES,
-                           &tmO1, g.N));
+                           &p1, g.N));
+    if (g.epilogue == EPI_RELU_ACT) { tmO0 = p0; tmO1 = p1; tmO2 = p1; }
+    else { tmO1 = p0; tmO2 = p1; }
   } else {
-    RB_TRY(tensor_map_2d(g.C, g.M, g.N, 32, 4, &tmO0, g.ldc));
     tmO1 = tmO0;
+    tmO2 = tmO0;
   }
   const int num_n_tiles = ceil_div(g.N, BN);
   const int num_tiles = ceil_div(g.M, 2 * BM) * num_n_tiles;
@@ -469,8 +588,8 @@ int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
   }
   dim3 grid(2 * (num_tiles < sm_pairs ? num_tiles : sm_pairs));
   const int fmt = ELEM_BYTES == 4 ? 2 : (prec_is_fp16(g.mode) ? 0 : 1);
-  RB_CUDA(launch_pdl(kern, grid, dim3(kThreads), cfg::SMEM, s, tmA, tmW, tmO0, tmO1, g.act.overflow,
-                     (int)prec_is_fp16(g.mode), (int)g.M, (int)g.N, (int)g.K, (int)a_plane_rows, (int)w_plane_rows,
+  RB_CUDA(launch_pdl(kern, grid, dim3(kThreads), cfg::SMEM, s, tmA, tmW, tmO0, tmO1, tmO2, (const float*)g.C, g.ldc,
+                     g.nf, g.act.overflow, (int)prec_is_fp16(g.mode), (int)g.M, (int)g.N, (int)g.K, (int)a_plane_rows, (int)w_plane_rows,
                      g.epilogue, make_idesc_pair(fmt, BN), g.out_scale, num_n_tiles, num_tiles, g_gemm_trace));
   launch_count()++;
   return 0;

@@ -78,77 +78,6 @@ __global__ void rmsnorm_kernel(const float* __restrict__ x, const float* __restr
 }
 
 // ------------------------------------------------------------------------------------------------
-// row-wise attention: one CTA per query row, thread c owns float4 chunk c of the inner dimension, the
-// 16 threads of a head reduce the q.k dot products with shuffles; scores live in shared memory.
-// ------------------------------------------------------------------------------------------------
-template <typename KPtr, typename VPtr, typename Valid, typename Bias>
-__device__ __forceinline__ float4 attn_core(float4 q4, int h, int c, bool active, int H, int P, float* sc,
-                                            KPtr kptr, VPtr vptr, Valid valid, Bias bias) {
-  const int lane16 = threadIdx.x & 15;
-#pragma unroll 4
-  for (int p = 0; p < P; ++p) {
-    float part = 0.f;
-    const bool ok = valid(p);
-    if (ok && active) {
-      const float4 k4 = __ldg(kptr(p) + c);
-      part = q4.x * k4.x + q4.y * k4.y + q4.z * k4.z + q4.w * k4.w;
-    }
-    part += __shfl_xor_sync(0xffffffffu, part, 8);
-    part += __shfl_xor_sync(0xffffffffu, part, 4);
-    part += __shfl_xor_sync(0xffffffffu, part, 2);
-    part += __shfl_xor_sync(0xffffffffu, part, 1);
-    if (active && lane16 == 0) sc[h * P + p] = ok ? part + bias(h, p) : -INFINITY;
-  }
-  __syncthreads();
-  {   // softmax over the P positions of head h by its 16 threads (inactive lanes shadow head 0, read-only)
-    const int hs = active ? h : 0;
-    float m = -INFINITY;
-    for (int p = lane16; p < P; p += 16) m = fmaxf(m, sc[hs * P + p]);
-    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o, 16));
-    float sum = 0.f;
-    for (int p = lane16; p < P; p += 16) sum += expf(sc[hs * P + p] - m);
-    for (int o = 8; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o, 16);
-    __syncthreads();
-    if (active)
-      for (int p = lane16; p < P; p += 16) sc[h * P + p] = expf(sc[h * P + p] - m) / sum;
-  }
-  __syncthreads();
-  float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) {
-#pragma unroll 4
-    for (int p = 0; p < P; ++p) {
-      if (!valid(p)) continue;
-      const float pr = sc[h * P + p];
-      const float4 v4 = __ldg(vptr(p) + c);
-      o.x += pr * v4.x; o.y += pr * v4.y; o.z += pr * v4.z; o.w += pr * v4.w;
-    }
-  }
-  return o;
-}
-
-__global__ void enc_attn_kernel(EncAttnArgs a, ActOut ctx) {
-  extern __shared__ float smem[];
-  const int inner = a.H * 64, c4n = inner >> 2;
-  const int m = blockIdx.x, c = threadIdx.x;   // m = b*S + i
-  const bool active = c < c4n;
-  const int h = c >> 4;
-  const int b = m / a.S, i = m - b * a.S;
-  float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (active) q4 = reinterpret_cast<const float4*>(a.qkv + (int64_t)m * 3 * inner)[c];
-  const float* base = a.qkv + (int64_t)b * a.S * 3 * inner;
-  const int64_t* mk = a.mask + (int64_t)b * a.S;
-  const float* bias = a.bias;
-  const int S = a.S;
-  const int64_t ld = 3 * inner;
-  const float4 o = attn_core(
-      q4, h, c, active, a.H, a.S, smem,
-      [&](int p) { return reinterpret_cast<const float4*>(base + p * ld + inner); },
-      [&](int p) { return reinterpret_cast<const float4*>(base + p * ld + 2 * inner); },
-      [&](int p) { return mk[p] != 0; }, [&](int hh, int p) { return bias[hh * (2 * S - 1) + (p - i + S - 1)]; });
-  if (active) act_store4(ctx, (int64_t)m * inner + (int64_t)c * 4, o);
-}
-
-// ------------------------------------------------------------------------------------------------
 // fp32 FFMA GEMM: C[M,N] = A[M,K] * W[N,K]^T, 128x128x16 tiles, 8x8 per thread. Exact fp32 products and
 // fp32 accumulation: the reference-arithmetic mode and the yardstick the tensor-core modes are tested on.
 // ------------------------------------------------------------------------------------------------
@@ -208,9 +137,38 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const float* __restrict_
   }
 }
 
-__global__ void pack_planes_kernel(const float* __restrict__ src, ActOut out, int64_t numel, float scale) {
+__global__ void pack_planes_kernel(const float* __restrict__ src, ActOut out, int64_t numel, float scale,
+                                   const float* __restrict__ col_scale, int64_t k) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < numel) act_store(out, i, src[i] * scale);
+  if (i < numel) act_store(out, i, col_scale ? (src[i] * col_scale[i % k]) * scale : src[i] * scale);
+}
+
+// NormFold chain start: one warp per row; planes(x / r), and both parities of the partial-sum table
+__global__ void norm_init_kernel(const float* __restrict__ x, ActOut out, float* __restrict__ ss0,
+                                 float* __restrict__ ss1, int np, int64_t rows, int d, float eps) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  pdl_wait();
+  if (row >= rows) return;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * d);
+  const int d4 = d >> 2;
+  float ss = 0.f;
+  for (int c = lane; c < d4; c += 32) {
+    const float4 t = xr[c];
+    ss += t.x * t.x + t.y * t.y + t.z * t.z + t.w * t.w;
+  }
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  const float rs = 1.0f / sqrtf(ss / (float)d + eps);
+  pdl_trigger();
+  for (int c = lane; c < d4; c += 32) {
+    const float4 t = xr[c];
+    act_store4(out, row * d + (int64_t)c * 4, make_float4(t.x * rs, t.y * rs, t.z * rs, t.w * rs));
+  }
+  for (int i = lane; i < np; i += 32) {
+    const float v = i == 0 ? ss : 0.f;
+    ss0[row * np + i] = v;
+    ss1[row * np + i] = v;
+  }
 }
 
 }  // namespace
@@ -255,9 +213,7 @@ int launch_rmsnorm_f32(const float* x, const float* w, float* out, int64_t rows,
   return launch_rmsnorm_any<true>(x, w, ActOut{nullptr, 0, 0}, out, rows, d, eps, 1.0f, s);
 }
 
-static int attn_threads(int H) { return ((H * 16 + 31) / 32) * 32; }
-
-// attn_warp.cu: the decode-step attention kernels (one warp per (row, head))
+// attn_warp.cu: the attention kernels (one warp per (row, head)); the encoder reuses the cross-attention kernel
 bool launch_self_attn_warp(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s, int* status);
 bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, int* status);
 
@@ -275,16 +231,6 @@ int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s)
   return st;
 }
 
-int launch_enc_attn(const EncAttnArgs& a, ActOut ctx, cudaStream_t s) {
-  const int threads = attn_threads(a.H);
-  const size_t smem = (size_t)a.H * a.S * sizeof(float);
-  RB_REQUIRE(smem <= 48 * 1024, "H*S=%d too large for the encoder attention kernel", a.H * a.S);
-  enc_attn_kernel<<<a.B * a.S, threads, smem, s>>>(a, ctx);
-  RB_CUDA(cudaGetLastError());
-  rb::launch_count()++;
-  return 0;
-}
-
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t s) {
   RB_REQUIRE(g.K % 4 == 0, "K=%lld must be a multiple of 4", (long long)g.K);
   if (g.M == 0 || g.N == 0) return 0;
@@ -296,11 +242,25 @@ int launch_gemm_simt(const GemmArgs& g, cudaStream_t s) {
   return 0;
 }
 
+int launch_pack_planes_cols(const float* src, void* dst, int64_t numel, int64_t plane, int mode, float scale,
+                            const float* col_scale, int64_t k, int* overflow, cudaStream_t s) {
+  if (numel == 0) return 0;
+  pack_planes_kernel<<<ceil_div(numel, 256), 256, 0, s>>>(src, ActOut{dst, plane, mode, overflow}, numel, scale,
+                                                          col_scale, k);
+  RB_CUDA(cudaGetLastError());
+  rb::launch_count()++;
+  return 0;
+}
+
 int launch_pack_planes(const float* src, void* dst, int64_t numel, int64_t plane, int mode, float scale,
                        int* overflow, cudaStream_t s) {
-  if (numel == 0) return 0;
-  pack_planes_kernel<<<ceil_div(numel, 256), 256, 0, s>>>(src, ActOut{dst, plane, mode, overflow}, numel, scale);
-  RB_CUDA(cudaGetLastError());
+  return launch_pack_planes_cols(src, dst, numel, plane, mode, scale, nullptr, 1, overflow, s);
+}
+
+int launch_norm_init(const float* x, ActOut out, float* ss0, float* ss1, int np, int64_t rows, int d, float eps,
+                     cudaStream_t s) {
+  if (rows == 0) return 0;
+  RB_CUDA(launch_pdl(norm_init_kernel, dim3(ceil_div(rows, 8)), dim3(256), 0, s, x, out, ss0, ss1, np, rows, d, eps));
   rb::launch_count()++;
   return 0;
 }

@@ -6,9 +6,26 @@
 namespace rb {
 
 enum GemmEpilogue {
-  EPI_STORE = 0,     // C = acc                       (fp32)
-  EPI_RESIDUAL = 1,  // C = C + acc                   (fp32 residual stream)
-  EPI_RELU_ACT = 2   // act_out = relu(acc)           (ActBuf for the next GEMM: DenseReluDense.wi)
+  EPI_STORE = 0,       // C = acc                       (fp32)
+  EPI_RESIDUAL = 1,    // C = C + acc                   (fp32 residual stream)
+  EPI_RELU_ACT = 2,    // act_out = relu(acc)           (ActBuf for the next GEMM: DenseReluDense.wi)
+  EPI_RESID_NORM = 3   // C = C + acc, act_out = planes(C / r_prev), ss_out = per-row partial sums of C^2:
+                       // the residual add with the FOLLOWING T5LayerNorm folded in (see NormFold below)
+};
+
+// T5LayerNorm folded into the GEMMs around it (tensor-core modes). rmsnorm(x) * W^T = (1/r) * x * (W diag(ln))^T with
+// r = sqrt(mean(x^2) + eps): the layer-norm weight is folded into the weight matrix when it is packed, the residual
+// GEMM that produces x writes the operand planes of x / r_prev (r_prev = the row's r at the previous norm point, so
+// the planes stay O(1) for the 16-bit formats) plus per-row partial sums of x^2 (one per 64 output columns, so the
+// result does not depend on scheduling), and the consuming GEMM multiplies its accumulator rows by r_prev / r.
+// That removes the 37 standalone RMSNorm launches of a decoder step.
+struct NormFold {
+  const float* ss_prev = nullptr;   // [M, np] partial sums of x^2 at the previous norm point
+  const float* ss_cur = nullptr;    // [M, np] ... at this norm point (consumers only)
+  float* ss_out = nullptr;          // [M, np] written by EPI_RESID_NORM
+  int np = 0;                       // partial sums per row = d_model / 64
+  float inv_d = 0.f, eps = 0.f;
+  bool scaled = false;              // consumer: multiply accumulator rows by r_prev / r_cur
 };
 
 struct GemmArgs {
@@ -23,6 +40,7 @@ struct GemmArgs {
   int64_t M, N, K;
   int epilogue;
   float out_scale = 1.0f;  // accumulator multiplier (undoes the power-of-two pre-scale of fp16 weight planes)
+  NormFold nf;
 };
 
 // fp16 weight planes are stored multiplied by 2^8 so that the low plane stays in fp16's normal range
@@ -35,6 +53,9 @@ int launch_broadcast_row(const float* vec, float* x, int64_t rows, int d, cudaSt
 // T5LayerNorm: out = w * x * rsqrt(mean(x^2) + eps) * scale, written as an ActBuf
 int launch_rmsnorm(const float* x, const float* w, ActOut out, int64_t rows, int d, float eps, float scale,
                    cudaStream_t s);
+// first norm point of a chain under NormFold: out = planes(x / r), ss[0][row][:] = ss[1][row][:] = {sum x^2, 0, ...}
+int launch_norm_init(const float* x, ActOut out, float* ss0, float* ss1, int np, int64_t rows, int d, float eps,
+                     cudaStream_t s);
 // same, fp32 output (encoder last_hidden_state)
 int launch_rmsnorm_f32(const float* x, const float* w, float* out, int64_t rows, int d, float eps, cudaStream_t s);
 
@@ -50,21 +71,17 @@ struct SelfAttnArgs {
 int launch_self_attn_decode(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s);
 
 struct CrossAttnArgs {
-  const float* q;         // [M, inner]
+  const float* q;         // [M, q_ld] (q_ld = 0: rows of `inner` floats)
   const float* kv;        // cross K/V of all layers [B*S, ld]; this layer's K at k_off, V at v_off
   int64_t ld, k_off, v_off;
   const int64_t* mask;    // [B, S] encoder attention mask
   int M, H, S, rows_per_query;
+  int64_t q_ld = 0;
+  // encoder self-attention through the same kernel: the "beams" are the S query rows of the sequence and every score
+  // gets the relative position bias rel_bias[h][(key - query) + S - 1]
+  const float* rel_bias = nullptr;
 };
 int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s);
-
-struct EncAttnArgs {
-  const float* qkv;       // [B*S, 3*inner]
-  const int64_t* mask;    // [B, S]
-  const float* bias;      // [H, 2*S-1] relative position bias by (key - query) + S - 1
-  int B, S, H;
-};
-int launch_enc_attn(const EncAttnArgs& a, ActOut ctx, cudaStream_t s);
 
 // fp32 FFMA GEMM (RB200_PREC_FP32) and the tcgen05 GEMM family (all other modes)
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t s);
@@ -77,6 +94,9 @@ inline int launch_gemm(const GemmArgs& g, cudaStream_t s) {
 // every element is multiplied by `scale` first; `overflow` (device int, may be null) is raised by fp16 planes
 int launch_pack_planes(const float* src, void* dst, int64_t numel, int64_t plane, int mode, float scale,
                        int* overflow, cudaStream_t s);
+// same with a per-column factor (row length k): dst = planes(src * scale * col_scale[col]) - layer norm folding
+int launch_pack_planes_cols(const float* src, void* dst, int64_t numel, int64_t plane, int mode, float scale,
+                            const float* col_scale, int64_t k, int* overflow, cudaStream_t s);
 
 // HF T5 relative position bucket (host; float32 arithmetic like torch)
 int relative_bucket(int rel, bool bidirectional, int num_buckets, int max_distance);

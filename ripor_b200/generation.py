@@ -88,32 +88,56 @@ def generate_for_constrained_prefix_beam_search(model, valid_smtids, inputs: Opt
     base = getattr(model, "base_model", model)
     trie: DocidTrie = valid_smtids.trie
     B, S = input_ids.shape
-    engine = base.get_engine(B, num_beams, S, precision)
-    dev_index = engine.key[0]
-    trie.upload(dev_index)
-    L = _lib.lib()
-    n = B * num_return_sequences
     ids = input_ids.to(torch.int64).contiguous()
     mask = attention_mask.to(torch.int64).contiguous()
-    with torch.cuda.device(dev_index):
-        stream = _lib.stream_ptr()
-        if ids.is_cuda:
-            seqs = torch.empty((n, max_new_tokens + 1), dtype=torch.int64, device=ids.device)
-            scores = torch.empty((n,), dtype=torch.float32, device=ids.device)
-            leaf = torch.empty((n, 2), dtype=torch.int32, device=ids.device)
-            _lib.check(L.rb200_engine_search(engine.h, trie.handle, ids.data_ptr(), mask.data_ptr(), B, S, num_beams,
-                                             max_new_tokens, num_return_sequences, int(bool(apply_log_softmax_for_scores)),
-                                             seqs.data_ptr(), scores.data_ptr(), leaf.data_ptr(), stream))
-        else:
-            seqs = torch.empty((n, max_new_tokens + 1), dtype=torch.int64).pin_memory()
-            scores = torch.empty((n,), dtype=torch.float32).pin_memory()
-            leaf = torch.empty((n, 2), dtype=torch.int32).pin_memory()
-            _lib.check(L.rb200_engine_search_host(engine.h, trie.handle, ids.data_ptr(), mask.data_ptr(), B, S,
-                                                  num_beams, max_new_tokens, num_return_sequences,
-                                                  int(bool(apply_log_softmax_for_scores)), seqs.data_ptr(),
-                                                  scores.data_ptr(), leaf.data_ptr(), stream))
+    auto = (precision or base.precision) == "auto"
+    n = B * num_return_sequences
+    L = _lib.lib()
+    while True:
+        mode = base.resolve_precision(precision)
+        try:
+            engine = base.get_engine(B, num_beams, S, mode)
+        except ValueError as err:                                    # a WEIGHT does not fit the fp16 planes
+            if auto and mode == "fp16x3" and "fp16 range" in str(err):
+                base.fp16_ok = False
+                continue
+            raise
+        dev_index = engine.key[0]
+        trie.upload(dev_index)
+        with torch.cuda.device(dev_index):
+            stream = _lib.stream_ptr()
+            if ids.is_cuda:
+                seqs = torch.empty((n, max_new_tokens + 1), dtype=torch.int64, device=ids.device)
+                scores = torch.empty((n,), dtype=torch.float32, device=ids.device)
+                leaf = torch.empty((n, 2), dtype=torch.int32, device=ids.device)
+                _lib.check(L.rb200_engine_search(engine.h, trie.handle, ids.data_ptr(), mask.data_ptr(), B, S,
+                                                 num_beams, max_new_tokens, num_return_sequences,
+                                                 int(bool(apply_log_softmax_for_scores)), seqs.data_ptr(),
+                                                 scores.data_ptr(), leaf.data_ptr(), stream))
+            else:
+                # pinned staging buffers live with the engine (cudaHostAlloc costs milliseconds); the caller gets
+                # its own pageable copies, as the reference's `.cpu()` results are
+                key = (n, max_new_tokens + 1)
+                if getattr(engine, "host_out_key", None) != key:
+                    engine.host_out = (torch.empty((n, max_new_tokens + 1), dtype=torch.int64).pin_memory(),
+                                       torch.empty((n,), dtype=torch.float32).pin_memory(),
+                                       torch.empty((n, 2), dtype=torch.int32).pin_memory())
+                    engine.host_out_key = key
+                pseqs, pscores, pleaf = engine.host_out
+                _lib.check(L.rb200_engine_search_host(engine.h, trie.handle, ids.data_ptr(), mask.data_ptr(), B, S,
+                                                      num_beams, max_new_tokens, num_return_sequences,
+                                                      int(bool(apply_log_softmax_for_scores)), pseqs.data_ptr(),
+                                                      pscores.data_ptr(), pleaf.data_ptr(), stream))
+                seqs, scores, leaf = pseqs.clone(), pscores.clone(), pleaf.clone()
+        # fp16x3 poisons EVERY score with NaN when an activation left the fp16 range: in auto mode look at one
+        # element (4-byte read) and redo the batch in tf32x3; explicit fp16x3 hands the NaNs to the caller
+        if auto and mode == "fp16x3" and bool(torch.isnan(scores[:1]).item()):
+            base.fp16_ok = False
+            continue
+        break
     out = BeamSearchEncoderDecoderOutput(seqs, scores, leaf)
     out.gpu_launches = int(L.rb200_engine_last_launch_count(engine.h))
+    out.precision = mode
     if return_dict_in_generate is False:
         return seqs
     return out

@@ -108,8 +108,11 @@ class T5ForDocIDGeneration:
         self.config = config
         self._weights = {k: v for k, v in state_dict.items()}
         self._device: Optional[int] = None
-        self._engine: Optional[_Engine] = None
-        self.precision = os.environ.get("RB200_PRECISION", "tf32x3")
+        self._engines: Dict[str, _Engine] = {}
+        # "auto" = fp16x3 (fp32-grade 3-MMA split on 11-bit fp16 planes, the fastest parity-safe mode) with an
+        # automatic re-run in tf32x3 (same mantissa, fp32 exponent range) when a value leaves the fp16 range
+        self.precision = os.environ.get("RB200_PRECISION", "auto")
+        self.fp16_ok = True
 
     # -- nn.Module look-alikes the reference callers use -------------------------------------------
     def eval(self):
@@ -136,18 +139,28 @@ class T5ForDocIDGeneration:
         if not torch.cuda.is_available():
             raise _lib.RB200Error("no CUDA device: the retrieval path has no CPU fallback")
         precision = precision or self.precision
+        if precision == "auto":
+            raise ValueError("resolve 'auto' with resolve_precision() first")
         dev = self._device if self._device is not None else torch.cuda.current_device()
-        e = self._engine
+        e = self._engines.get(precision)
         if e is not None:
             d0, mb, nb, ms, pr = e.key
-            if d0 == dev and nb == num_beams and pr == precision and mb >= batch and ms >= src_len:
+            if d0 == dev and nb == num_beams and mb >= batch and ms >= src_len:
                 return e
-            self._engine = None
+            del self._engines[precision]
             del e
             torch.cuda.synchronize()
         with torch.cuda.device(dev):
-            self._engine = _Engine(self.config, self._weights, dev, batch, num_beams, max(src_len, 8), precision)
-        return self._engine
+            self._engines[precision] = _Engine(self.config, self._weights, dev, batch, num_beams, max(src_len, 8),
+                                               precision)
+        return self._engines[precision]
+
+    def resolve_precision(self, precision: Optional[str] = None) -> str:
+        """'auto' -> 'fp16x3' until an fp16 range overflow has been seen on this model, then 'tf32x3'."""
+        precision = precision or self.precision
+        if precision != "auto":
+            return precision
+        return "fp16x3" if self.fp16_ok else "tf32x3"
 
     @classmethod
     def from_pretrained(cls, path: str, config: Optional[T5forDocIDConfig] = None) -> "T5ForDocIDGeneration":

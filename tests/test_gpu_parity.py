@@ -254,7 +254,10 @@ def test_fp16x3_overflow_is_loud():
     dims = syn.T5Dims.tiny()
     w = syn.make_weights(dims)
     w = dict(w)
-    w["decoder.block.0.layer.0.layer_norm.weight"] = w["decoder.block.0.layer.0.layer_norm.weight"] * 1e5
+    # weights that still fit the fp16 planes (|w| * 2^8 < 65504) but whose activations do not: the layer norm gain
+    # puts the normalised input at ~150 and wi (std ~22) lifts the FFN hidden state to ~1e5 > 65504
+    w["decoder.block.0.layer.2.layer_norm.weight"] = w["decoder.block.0.layer.2.layer_norm.weight"] * 150
+    w["decoder.block.0.layer.2.DenseReluDense.wi.weight"] = w["decoder.block.0.layer.2.DenseReluDense.wi.weight"] * 250
     codes = syn.make_codes(400, dims.docid_len, dims.decoder_vocab_size)
     ids, mask = syn.make_queries(2, S=12, vocab_size=dims.vocab_size)
     model = T5SeqAQEncoder.from_weights(dims, w)
@@ -263,6 +266,10 @@ def test_fp16x3_overflow_is_loud():
     assert torch.isnan(out.sequences_scores).all()
     out = _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="tf32x3")
     assert not torch.isnan(out.sequences_scores).any()
+    # precision="auto" starts in fp16x3, sees the poisoned scores and redoes the batch in tf32x3
+    auto = _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="auto")
+    assert auto.precision == "tf32x3" and model.base_model.fp16_ok is False
+    assert torch.equal(auto.sequences, out.sequences) and torch.equal(auto.sequences_scores, out.sequences_scores)
     # a weight that does not fit fp16 after the 2^8 pre-scale is refused when the engine is built
     w["decoder.block.0.layer.2.DenseReluDense.wi.weight"] = w["decoder.block.0.layer.2.DenseReluDense.wi.weight"] * 3e4
     with pytest.raises(ValueError, match="fp16 range"):

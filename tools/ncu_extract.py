@@ -1,0 +1,51 @@
+"""Summarise an ncu --set full report (read here with `ncu -i ... --page raw --csv`) into a few per-kernel numbers:
+duration, DRAM bytes, L2->SM bytes, tensor-pipe activity, issue activity, occupancy."""
+import csv
+import json
+import subprocess
+import sys
+
+WANT = {
+    "gpu__time_duration.sum": "us",
+    "dram__bytes_read.sum": "dram_read",
+    "dram__bytes_write.sum": "dram_write",
+    "l1tex__m_xbar2l1tex_read_bytes.sum": "l2_to_sm",
+    "sm__pipe_tensor_subpipe_op_utcmma_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pct",
+    "sm__inst_executed_pipe_tensor_op_utcmma.sum": "utcmma",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_pct",
+    "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_pct",
+    "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
+    "launch__grid_size": "grid",
+    "launch__registers_per_thread": "regs",
+}
+
+
+def to_bytes(v, unit):
+    v = float(v.replace(",", ""))
+    return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+
+
+def main(path):
+    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(raw.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    out = []
+    for r in rows[2:]:
+        d = {"kernel": r[idx["Kernel Name"]].split("(")[0].split("::")[-1][:60]}
+        for k, name in WANT.items():
+            if k in idx and r[idx[k]] != "":
+                u = units[idx[k]]
+                if "byte" in u:
+                    d[name] = to_bytes(r[idx[k]], u)
+                else:
+                    v = float(r[idx[k]].replace(",", ""))
+                    if name == "us":
+                        v = v / 1e3 if u in ("ns", "nsecond") else v
+                    d[name] = v
+        out.append(d)
+    print(json.dumps(out, indent=1))
+
+
+if __name__ == "__main__":
+    main(sys.argv[1])
