@@ -215,6 +215,7 @@ def run_ours(a):
         out = step(True)
     launches_per_step = out.gpu_launches
     prec = out.precision                      # what 'auto' resolved to
+    tail_from = out.forced_tail_from
     # ---- timed region: K steps, inputs resident in HBM -------------------------------------------------
     sampler = ClockSampler(local)
     sync_all()
@@ -283,7 +284,7 @@ def run_ours(a):
                   "tf32": "tf32", "bf16": "bf16"}[prec],
         "data": "synthetic",
         "config": {"workload": workload_name(a), "precision": prec, "precision_requested": a.precision,
-                   "global_batch": world * B,
+                   "global_batch": world * B, "forced_tail_from_step": tail_from,
                    "l2": "per-step working set (fp32 KV cache + weights, >6 GB) exceeds the 126 MB L2",
                    "trie_build_s": round(trie_build_s, 2), "parallelism": f"query-sharded x{world}"},
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps), "roofline": roofline}

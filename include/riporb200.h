@@ -195,6 +195,11 @@ int rb200_engine_decode_step(rb200_engine* eng, const rb200_beam* beam, int t, f
 int rb200_engine_beam(rb200_engine* eng, rb200_beam** beam);
 /* number of kernel launches issued by the last rb200_engine_search* call. */
 int64_t rb200_engine_last_launch_count(const rb200_engine* eng);
+/* Forced tail: once every beam of a batch sits on a single trie leaf, the rest of its DocID is determined, and the
+ * engine evaluates the remaining positions of all beams in one teacher-forced pass (same per-row arithmetic as the
+ * step loop of generation.py:423-530, far fewer and larger kernels). Returns the decode step at which the last
+ * search switched, or -1 if it ran step by step to the end (RB200_TAIL=0 disables the switch). */
+int rb200_engine_last_tail_step(const rb200_engine* eng);
 /* Measurement aid for bench.py's roofline leg: with profiling on, every GEMM launch of the engine is
  * bracketed by CUDA events on its stream. get_profile synchronises and returns the summed GEMM device time
  * (ms), the algorithmic FLOPs (2*M*N*K per launch) and the launch count since profiling was switched on. */

@@ -68,6 +68,7 @@ SIGNATURES = {
     "rb200_engine_decode_step": (C.c_int, [c_void_p, c_void_p, C.c_int, c_void_p, c_void_p]),
     "rb200_engine_beam": (C.c_int, [c_void_p, P(c_void_p)]),
     "rb200_engine_last_launch_count": (c_i64, [c_void_p]),
+    "rb200_engine_last_tail_step": (C.c_int, [c_void_p]),
     "rb200_engine_set_profiling": (C.c_int, [c_void_p, C.c_int]),
     "rb200_engine_get_profile": (C.c_int, [c_void_p, P(c_f64), P(c_f64), P(c_i64)]),
     "rb200_relative_position_bucket": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),

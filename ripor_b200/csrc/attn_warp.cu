@@ -226,6 +226,89 @@ __global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArg
   pdl_trigger();
 }
 
+// Forced tail: all T remaining positions of a beam row in one task. The K/V rows of the whole lineage (cached
+// prefix + the T new positions) are staged once and serve T queries; the lane that owns key position p keeps its K
+// row in registers across the queries.
+constexpr int kTailWarpFloats = 32 * 64 * 3 + 32;          // K | V | q rows of up to 32 positions | exp(scores)
+
+__global__ void __launch_bounds__(kWarps * 32, 2) self_attn_tail_kernel(TailAttnArgs a, ActOut ctx) {
+  extern __shared__ __align__(16) float tsmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;
+  float* ks = tsmem + warp * kTailWarpFloats;
+  float* vs = ks + 32 * 64;
+  float* qs = vs + 32 * 64;
+  float* es = qs + 32 * 64;
+  const int inner = a.H * 64, t = a.t, T = a.T, L = a.L, R = a.R;
+  const int P = t + T;                                              // positions of the finished lineage (<= 32)
+  const int ntask = R * a.H;
+  pdl_wait();
+  for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += gridDim.x * kWarps) {
+    const int r = wid / a.H, h = wid - r * a.H;
+    __syncwarp();
+    // ---- stage K, V of every position and q of the T new ones ------------------------------------------------------
+    const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
+    for (int rr = 0; rr < 16; ++rr) {
+      const int p = 2 * rr + half;
+      const int slot = __shfl_sync(0xffffffffu, slot_l, p);
+      if (p < P) {
+        const float* kp;
+        const float* vp;
+        if (p < t) {
+          kp = a.cache_k + (int64_t)slot * inner + h * 64 + l16 * 4;
+          vp = a.cache_v + (int64_t)slot * inner + h * 64 + l16 * 4;
+        } else {
+          const float* row = a.qkv + ((int64_t)(p - t) * R + r) * 3 * inner + h * 64 + l16 * 4;
+          kp = row + inner;
+          vp = row + 2 * inner;
+          cp_async16_on(qs + (p - t) * 64 + l16 * 4, row);
+        }
+        cp_async16_on(ks + p * 64 + ((l16 ^ (p & 7)) << 2), kp);
+        cp_async16_on(vs + p * 64 + l16 * 4, vp);
+      } else {
+        *reinterpret_cast<float4*>(vs + p * 64 + l16 * 4) = make_float4(0.f, 0.f, 0.f, 0.f);   // never 0 * garbage
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    float4 k4[16];                                                  // this lane's key row (position = lane)
+#pragma unroll
+    for (int j = 0; j < 16; ++j)
+      k4[j] = lane < P ? *reinterpret_cast<const float4*>(ks + lane * 64 + ((j ^ (lane & 7)) << 2))
+                       : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = 0; j < T; ++j) {
+      const int pq = t + j;                                         // position of this query
+      float acc = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc = dot4(*reinterpret_cast<const float4*>(qs + j * 64 + c * 4), k4[c], acc);
+      const float sc = lane <= pq ? acc + __ldg(a.bias + h * L + (pq - lane)) : -INFINITY;
+      const float mx = warp_max(sc);
+      const float e = expf(sc - mx);                                // 0 beyond the query's own position
+      const float sum = warp_sum(e);
+      __syncwarp();
+      es[lane] = e;
+      __syncwarp();
+      float2 o2 = make_float2(0.f, 0.f);
+      const int ng = (pq + 4) >> 2;
+      for (int g = 0; g < ng; ++g) {
+        const float4 e4 = *reinterpret_cast<const float4*>(es + 4 * g);
+        const float2 v0 = *reinterpret_cast<const float2*>(vs + (4 * g + 0) * 64 + lane * 2);
+        const float2 v1 = *reinterpret_cast<const float2*>(vs + (4 * g + 1) * 64 + lane * 2);
+        const float2 v2 = *reinterpret_cast<const float2*>(vs + (4 * g + 2) * 64 + lane * 2);
+        const float2 v3 = *reinterpret_cast<const float2*>(vs + (4 * g + 3) * 64 + lane * 2);
+        o2.x = fmaf(e4.x, v0.x, o2.x); o2.y = fmaf(e4.x, v0.y, o2.y);
+        o2.x = fmaf(e4.y, v1.x, o2.x); o2.y = fmaf(e4.y, v1.y, o2.y);
+        o2.x = fmaf(e4.z, v2.x, o2.x); o2.y = fmaf(e4.z, v2.y, o2.y);
+        o2.x = fmaf(e4.w, v3.x, o2.x); o2.y = fmaf(e4.w, v3.y, o2.y);
+      }
+      const float inv = 1.0f / sum;
+      act_store2(ctx, ((int64_t)j * R + r) * inner + h * 64 + lane * 2, make_float2(o2.x * inv, o2.y * inv));
+    }
+  }
+  pdl_trigger();
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // cross-attention against the query's encoder K/V
 // ------------------------------------------------------------------------------------------------------------
@@ -258,7 +341,7 @@ __global__ void __launch_bounds__(kWarps * 32, XB <= 5 ? 3 : 2) cross_attn_warp_
   const int inner = a.H * 64;
   const int i0 = blockIdx.y * kXB;
   const int nact = min(kXB, rpq - i0);
-  const int64_t row0 = (int64_t)b * rpq + i0;
+  const int64_t row0 = (int64_t)blockIdx.z * a.block_rows + (int64_t)b * rpq + i0;
   const int64_t* mk = a.mask + (int64_t)b * S;
   // q rows of this warp's beams -> shared memory (joins the first K commit group); rows beyond nact repeat row 0
   const int64_t q_ld = a.q_ld ? a.q_ld : inner;
@@ -416,7 +499,7 @@ bool launch_self_attn_warp(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s, in
 template <bool QS, int XB>
 static cudaError_t launch_cross_cfg(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s) {
   const int B = a.M / a.rows_per_query;
-  const dim3 grid(ceil_div((int64_t)B * a.H, kWarps), ceil_div(a.rows_per_query, XB)), block(kWarps * 32);
+  const dim3 grid(ceil_div((int64_t)B * a.H, kWarps), ceil_div(a.rows_per_query, XB), a.nblocks), block(kWarps * 32);
   constexpr size_t smem = (size_t)kWarps * x_warp_floats<QS, XB>() * sizeof(float);
   auto kern = cross_attn_warp_kernel<QS, XB>;
   static bool attr_set = false;
@@ -426,6 +509,25 @@ static cudaError_t launch_cross_cfg(const CrossAttnArgs& a, ActOut ctx, cudaStre
     attr_set = true;
   }
   return launch_pdl(kern, grid, block, smem, s, a, ctx);
+}
+
+int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s) {
+  RB_REQUIRE(a.t >= 1 && a.T >= 1 && a.t + a.T <= 32, "forced tail needs 1 <= t and t + T <= 32 (t=%d, T=%d)", a.t, a.T);
+  constexpr size_t smem = (size_t)kWarps * kTailWarpFloats * sizeof(float);
+  static bool attr_set = false;
+  static int sms = 0;
+  if (!attr_set) {
+    RB_CUDA(cudaFuncSetAttribute(self_attn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int dev = 0;
+    RB_CUDA(cudaGetDevice(&dev));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    attr_set = true;
+  }
+  const int want = ceil_div((int64_t)a.R * a.H, kWarps);
+  const dim3 grid(want < 2 * sms ? want : 2 * sms), block(kWarps * 32);
+  RB_CUDA(launch_pdl(self_attn_tail_kernel, grid, block, smem, s, a, ctx));
+  launch_count()++;
+  return 0;
 }
 
 bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, int* status) {

@@ -46,6 +46,7 @@ struct StepArgs {
   int32_t* token_out;
   const float* embed_table;
   float* next_x;
+  int32_t* not_forced;
 };
 
 template <int THREADS>
@@ -158,7 +159,9 @@ __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
     a.sc_new[r_new] = win_val[j];
     a.parent_out[r_new] = i;
     a.token_out[r_new] = v;
-    a.st_new[r_new] = rb::trie_child(a.tv, a.st_old[b * nb + i], t, v);
+    const TrieState ns = rb::trie_child(a.tv, a.st_old[b * nb + i], t, v);
+    a.st_new[r_new] = ns;
+    if (ns.hi - ns.lo != 1) atomicAdd(a.not_forced, 1);   // not (yet) a single leaf: the tail cannot be forced
   }
   const int L = a.L;
   for (int e = tid; e < nb * L; e += THREADS) {
@@ -218,7 +221,73 @@ __global__ void beam_finalize_kernel(int nb, int L, int steps, int keep, double 
   }
 }
 
+// forced tail: one CTA per beam row
+__global__ void tail_prepare_kernel(TrieView tv, int t, int T, int R, int L, int d, const TrieState* __restrict__ st,
+                                    int32_t* __restrict__ hist, const float* const* __restrict__ in_tabs,
+                                    float* __restrict__ x) {
+  const int r = blockIdx.x;
+  const int64_t leaf = st[r].lo;
+  for (int j = threadIdx.x; j < T; j += blockDim.x) hist[r * L + t + j] = rb::trie_code(tv, leaf, t + j);
+  const int d4 = d >> 2;
+  for (int j = 1; j < T; ++j) {
+    const int tok = rb::trie_code(tv, leaf, t + j - 1);            // input of position t+j = token chosen at t+j-1
+    const float4* src = reinterpret_cast<const float4*>(in_tabs[t + j - 1] + (int64_t)tok * d);
+    float4* dst = reinterpret_cast<float4*>(x + ((int64_t)j * R + r) * d);
+    for (int c = threadIdx.x; c < d4; c += blockDim.x) dst[c] = src[c];
+  }
+}
+
+__global__ void tail_finish_kernel(TrieView tv, int t, int T, int R, int V, int apply_ls,
+                                   const float* __restrict__ logits, const TrieState* __restrict__ st,
+                                   double* __restrict__ sc) {
+  // one warp per row; the float64 adds happen in step order, exactly as the step-by-step loop would do them
+  const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= R) return;
+  const int64_t leaf = st[r].lo;
+  double s = sc[r];
+  for (int j = 0; j < T; ++j) {
+    const float* row = logits + ((int64_t)j * R + r) * V;
+    float x = row[rb::trie_code(tv, leaf, t + j)];
+    if (apply_ls) {
+      float m = -INFINITY;
+      for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int v = lane; v < V; v += 32) sum += expf(row[v] - m);
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      x = (x - m) - logf(sum);
+    }
+    s += (double)x;
+  }
+  if (lane == 0) sc[r] = s;
+}
+
 }  // namespace
+
+namespace rb {
+
+int launch_tail_prepare(rb200_beam* bm, const rb200_trie* trie, int T, const float* const* in_tabs_dev, float* x,
+                        int d_model, cudaStream_t s) {
+  const int R = bm->batch * bm->nb;
+  tail_prepare_kernel<<<R, 128, 0, s>>>(trie->device_view(), bm->step, T, R, bm->L, d_model, bm->state[bm->cur],
+                                        bm->hist[bm->cur], in_tabs_dev, x);
+  RB_CUDA(cudaGetLastError());
+  launch_count()++;
+  return 0;
+}
+
+int launch_tail_finish(rb200_beam* bm, const rb200_trie* trie, int T, const float* logits, int apply_log_softmax,
+                       cudaStream_t s) {
+  const int R = bm->batch * bm->nb;
+  tail_finish_kernel<<<ceil_div(R, 4), 128, 0, s>>>(trie->device_view(), bm->step, T, R, bm->V, apply_log_softmax,
+                                                    logits, bm->state[bm->cur], bm->scores[bm->cur]);
+  RB_CUDA(cudaGetLastError());
+  launch_count()++;
+  bm->step += T;
+  return 0;
+}
+
+}  // namespace rb
 
 extern "C" {
 
@@ -240,6 +309,7 @@ int rb200_beam_create(int device, int max_batch, int num_beams, int L, int V, rb
     RB_CUDA(cudaMalloc(&bm->hist[h], R * L * sizeof(int32_t)));
     RB_CUDA(cudaMalloc(&bm->anc[h], R * L * sizeof(int32_t)));
   }
+  RB_CUDA(cudaMalloc(&bm->not_forced, sizeof(int32_t)));
   RB_CUDA(cudaMalloc(&bm->parent, R * sizeof(int32_t)));
   RB_CUDA(cudaMalloc(&bm->token, R * sizeof(int32_t)));
   RB_CUDA(cudaSetDevice(prev));
@@ -252,7 +322,7 @@ int rb200_beam_free(rb200_beam* bm) {
   for (int h = 0; h < 2; ++h) {
     cudaFree(bm->scores[h]); cudaFree(bm->state[h]); cudaFree(bm->hist[h]); cudaFree(bm->anc[h]);
   }
-  cudaFree(bm->parent); cudaFree(bm->token);
+  cudaFree(bm->parent); cudaFree(bm->token); cudaFree(bm->not_forced);
   delete bm;
   return 0;
 }
@@ -291,6 +361,8 @@ int rb200_beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits,
   a.sc_new = bm->scores[n]; a.st_new = bm->state[n]; a.hist_new = bm->hist[n]; a.anc_new = bm->anc[n];
   a.parent_out = bm->parent; a.token_out = bm->token;
   a.embed_table = embed_table; a.next_x = next_x;
+  a.not_forced = bm->not_forced;
+  RB_CUDA(cudaMemsetAsync(bm->not_forced, 0, sizeof(int32_t), (cudaStream_t)stream));
   const int nb = bm->nb;
   const size_t smem = (2 * nb + 32) * sizeof(double) + (32 + nb) * sizeof(int) + 2 * nb * sizeof(float) +
                       (size_t)nb * a.tv.words * sizeof(uint32_t);

@@ -15,4 +15,18 @@ struct rb200_beam {
   int32_t* anc[2] = {nullptr, nullptr};         // [R, L] anc[r][p] = row whose K/V at position p belongs to r's lineage
   int32_t* parent = nullptr;                    // [R] in-query beam index chosen at the last step
   int32_t* token = nullptr;                     // [R] token chosen at the last step
+  int32_t* not_forced = nullptr;                // [1] rows of the current state whose trie range is not a single leaf
 };
+
+// ---- forced tail (engine.cu) --------------------------------------------------------------------------------------
+// Once every beam of the batch sits on a single leaf range, the rest of its DocID is determined by the trie: the
+// remaining T steps are evaluated in ONE teacher-forced pass over T*R rows (position-major: row = j*R + r).
+namespace rb {
+// x[(j*R + r), :] = list_decoder_embeds[t+j-1][code(r, t+j-1)] for j = 1..T-1 (block 0 was written by the last beam
+// step) and hist[r][t..t+T-1] = the forced tokens
+int launch_tail_prepare(rb200_beam* bm, const rb200_trie* trie, int T, const float* const* in_tabs_dev, float* x,
+                        int d_model, cudaStream_t s);
+// beam score += the forced tokens' logits in step order (float64, like generation.py:463); advances the state to L
+int launch_tail_finish(rb200_beam* bm, const rb200_trie* trie, int T, const float* logits, int apply_log_softmax,
+                       cudaStream_t s);
+}  // namespace rb

@@ -101,6 +101,11 @@ struct rb200_engine {
   double prof_flops = 0.0;
 
   int* overflow = nullptr;         // device flags: [0] activation overflow of the batch in flight, [1] weights
+  // forced tail (beam.h): once every beam sits on a single trie leaf, the remaining positions run as one pass
+  bool tail = false;
+  float** in_tab_dev = nullptr;    // [Lmodel] device copy of in_tab
+  int32_t* flag_host = nullptr;    // pinned
+  int last_tail_from = -1;         // step at which the last search switched to the forced tail (-1: never)
 
   ActOut act(const Lane& l, void* base, int64_t row_len) const {
     return ActOut{base, l.Mcap * row_len, mode, overflow};
@@ -287,6 +292,11 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
     e->fold = e->mode != RB200_PREC_FP32 && d % 64 == 0 && (f && f[0] == '1') && !(gk && strcmp(gk, "1cta") == 0);
     e->np = d / 64;
   }
+  {
+    const char* tl = getenv("RB200_TAIL");
+    e->tail = e->Lmodel <= 32 && !(tl && tl[0] == '0');
+    RB_CUDA(cudaMallocHost((void**)&e->flag_host, sizeof(int32_t)));
+  }
   // workspaces: lane 0 can hold a whole batch, lane 1 the second half of a split one
   const int64_t pe = (int64_t)e->planes * e->elem;
   {
@@ -300,14 +310,15 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
     const int lane_batch = li == 0 ? cfg->max_batch : cfg->max_batch / 2;
     l.Rcap = (int64_t)lane_batch * cfg->max_beams;
     l.BScap = (int64_t)lane_batch * cfg->max_src_len;
-    l.Mcap = std::max(l.Rcap, l.BScap);
+    // the forced tail runs up to Lmodel positions of every beam row in one pass (lane 0 only)
+    l.Mcap = std::max((li == 0 && e->tail) ? l.Rcap * e->Lmodel : l.Rcap, l.BScap);
     RB_TRY(dev_alloc(e, (void**)&l.x, l.Mcap * d * 4));
     RB_TRY(dev_alloc(e, &l.xn, l.Mcap * d * pe));
     RB_TRY(dev_alloc(e, (void**)&l.qkv, l.Mcap * 3 * inner * 4));
     RB_TRY(dev_alloc(e, (void**)&l.q2, l.Mcap * inner * 4));
     RB_TRY(dev_alloc(e, &l.ctx, l.Mcap * inner * pe));
     RB_TRY(dev_alloc(e, &l.hbuf, l.Mcap * dff * pe));
-    RB_TRY(dev_alloc(e, (void**)&l.logits, l.Rcap * e->V * 4));
+    RB_TRY(dev_alloc(e, (void**)&l.logits, ((li == 0 && e->tail) ? l.Mcap : l.Rcap) * e->V * 4));
     RB_TRY(dev_alloc(e, (void**)&l.cross_kv, l.BScap * cfg->num_decoder_layers * 2 * inner * 4));
     RB_TRY(dev_alloc(e, (void**)&l.enc_out, l.BScap * d * 4));
     const int64_t cache = (int64_t)cfg->num_decoder_layers * e->Lmodel * l.Rcap * inner * 4;
@@ -358,6 +369,8 @@ int rb200_engine_free(rb200_engine* e) {
     if (l.own_stream) cudaStreamDestroy(l.own_stream);
   }
   if (e->fork) cudaEventDestroy(e->fork);
+  cudaFree(e->in_tab_dev);
+  if (e->flag_host) cudaFreeHost(e->flag_host);
   for (auto& st : e->stash) cudaFree(st.src);
   for (auto ev : e->events) cudaEventDestroy(ev);
   delete e;
@@ -489,6 +502,10 @@ int rb200_engine_finalize_weights(rb200_engine* e, void* stream) {
   }
   for (const auto& n : need)
     if (!e->have.count(n)) return rb::fail(RB200_ERR_STATE, "weight %s has not been set", n.c_str());
+  if (e->in_tab_dev == nullptr) {
+    RB_CUDA(cudaMalloc((void**)&e->in_tab_dev, e->in_tab.size() * sizeof(float*)));
+    RB_CUDA(cudaMemcpy(e->in_tab_dev, e->in_tab.data(), e->in_tab.size() * sizeof(float*), cudaMemcpyHostToDevice));
+  }
   // NormFold: every layer-norm vector is on the device now - pack W * diag(ln) for the matrices that follow one
   for (auto& st : e->stash) {
     char* dst = static_cast<char*>(st.w->ptr) + st.row0 * st.w->K * e->elem;
@@ -649,6 +666,50 @@ int lane_decode_step(rb200_engine* e, Lane& l, const rb200_beam* beam, int t, fl
   return 0;
 }
 
+// Forced tail: positions t .. t+T-1 of every beam row of the lane in one teacher-forced pass (rows position-major:
+// row = j * R + r). Same kernels and per-row arithmetic as T decoder steps; what changes is that the GEMMs see
+// T*R rows at once, a lineage's K/V are read once for all T queries, and ~130 launches replace ~130*T.
+int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, int t, int T, int apply_log_softmax, cudaStream_t s) {
+  rb200_beam* beam = l.beam;
+  const int R = l.B * l.nb;
+  const int64_t M = (int64_t)T * R;
+  const int d = e->d, inner = e->inner, dff = e->dff;
+  const float eps = e->cfg.layer_norm_eps;
+  RB_REQUIRE(M <= l.Mcap, "forced tail of %lld rows exceeds the lane capacity %lld", (long long)M, (long long)l.Mcap);
+  RB_TRY(rb::launch_tail_prepare(beam, trie, T, e->in_tab_dev, l.x, d, s));
+  const int64_t layer_cache = (int64_t)e->Lmodel * l.Rcap * inner;
+  for (size_t i = 0; i < e->dec.size(); ++i) {
+    Layer& w = e->dec[i];
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln0, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
+    rb::TailAttnArgs ta;
+    ta.qkv = l.qkv; ta.cache_k = l.cache_k + i * layer_cache; ta.cache_v = l.cache_v + i * layer_cache;
+    ta.anc = beam->anc[beam->cur]; ta.bias = e->dec_bias; ta.row_cap = l.Rcap;
+    ta.R = R; ta.H = e->H; ta.L = e->Lmodel; ta.t = t; ta.T = T;
+    RB_TRY(rb::launch_self_attn_tail(ta, e->act(l, l.ctx, inner), s));
+    RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
+    rb::CrossAttnArgs ca;
+    ca.q = l.q2; ca.kv = l.cross_kv + (int64_t)i * l.BScap * 2 * inner; ca.ld = 2 * inner; ca.k_off = 0;
+    ca.v_off = inner; ca.mask = l.cur_mask; ca.M = R; ca.H = e->H; ca.S = l.S; ca.rows_per_query = l.nb;
+    ca.nblocks = T; ca.block_rows = R;
+    RB_TRY(rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s));
+    RB_TRY(gemm(e, l, l.ctx, inner, w.co, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+    RB_TRY(rb::launch_rmsnorm(l.x, w.ln2, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), M, rb::EPI_RELU_ACT, s));
+    RB_TRY(gemm(e, l, l.hbuf, dff, w.wo, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+  }
+  const float scale = e->cfg.scaleup_output_hidden ? 1.0f / sqrtf((float)d) : 1.0f;
+  RB_TRY(rb::launch_rmsnorm(l.x, e->dec_final_ln, e->act(l, l.xn, d), M, d, eps, scale, s));
+  // LM head: the output table differs per position -> one GEMM per position block
+  for (int j = 0; j < T; ++j)
+    RB_TRY(gemm(e, l, static_cast<const char*>(l.xn) + (int64_t)j * R * d * e->elem, d, e->out_tab[t + j],
+                l.logits + (int64_t)j * R * e->V, e->V, ActOut{}, R, rb::EPI_STORE, s));
+  RB_TRY(rb::launch_tail_finish(beam, trie, T, l.logits, apply_log_softmax, s));
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -692,6 +753,8 @@ int rb200_engine_beam(rb200_engine* e, rb200_beam** beam) {
 
 int64_t rb200_engine_last_launch_count(const rb200_engine* e) { return e ? e->launches : 0; }
 
+int rb200_engine_last_tail_step(const rb200_engine* e) { return e ? e->last_tail_from : -1; }
+
 int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* ids, const int64_t* mask, int batch,
                         int S, int num_beams, int max_new_tokens, int num_return, int apply_log_softmax,
                         int64_t* sequences, float* scores, int32_t* leaf, void* stream) {
@@ -728,6 +791,10 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
     RB_TRY(lane_encode(e, l, ids + (int64_t)q0[li] * S, mask + (int64_t)q0[li] * S, nq, S, num_beams, ls[li]));
     RB_TRY(rb200_beam_reset(l.beam, trie, nq, ls[li]));
   }
+  // The forced tail needs a host decision: after each of the first steps the count of beams that are not yet on a
+  // single trie leaf comes back (4 bytes; the launch queue is ~a step ahead of the GPU, so the sync costs little).
+  const bool try_tail = e->tail && !e->fold && nl == 1 && max_new_tokens <= 32;
+  e->last_tail_from = -1;
   for (int t = 0; t < max_new_tokens; ++t) {
     const bool more = t + 1 < max_new_tokens;
     for (int li = 0; li < nl; ++li) {
@@ -735,6 +802,16 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
       RB_TRY(lane_decode_step(e, l, l.beam, t, l.logits, ls[li]));
       RB_TRY(rb200_beam_step(l.beam, trie, l.logits, t == 0 ? 1 : num_beams, apply_log_softmax,
                              more ? e->in_tab[t] : nullptr, more ? l.x : nullptr, e->d, ls[li]));
+    }
+    const int left = max_new_tokens - (t + 1);
+    if (try_tail && left >= 2 && t < 12) {
+      RB_CUDA(cudaMemcpyAsync(e->flag_host, e->lanes[0].beam->not_forced, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+      RB_CUDA(cudaStreamSynchronize(s0));
+      if (*e->flag_host == 0) {
+        RB_TRY(lane_tail(e, e->lanes[0], trie, t + 1, left, apply_log_softmax, s0));
+        e->last_tail_from = t + 1;
+        break;
+      }
     }
   }
   for (int li = 0; li < nl; ++li) {

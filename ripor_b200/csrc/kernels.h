@@ -77,11 +77,28 @@ struct CrossAttnArgs {
   const int64_t* mask;    // [B, S] encoder attention mask
   int M, H, S, rows_per_query;
   int64_t q_ld = 0;
+  // forced tail: nblocks position blocks of block_rows rows each (row = block * block_rows + query * rpq + beam)
+  int nblocks = 1;
+  int64_t block_rows = 0;
   // encoder self-attention through the same kernel: the "beams" are the S query rows of the sequence and every score
   // gets the relative position bias rel_bias[h][(key - query) + S - 1]
   const float* rel_bias = nullptr;
 };
 int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s);
+
+// Self-attention of the forced tail: T consecutive positions t..t+T-1 of every beam row in one launch. Rows are
+// position-major (row = j * R + r); positions < t come from the KV cache through the ancestry table, positions >= t
+// from the rows of this pass. Requires t + T <= 32.
+struct TailAttnArgs {
+  const float* qkv;       // [T*R, 3*inner]
+  const float* cache_k;   // this layer's cache [L, row_cap, inner]
+  const float* cache_v;
+  const int32_t* anc;     // [R, L]
+  const float* bias;      // [H, L]
+  int64_t row_cap;
+  int R, H, L, t, T;
+};
+int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s);
 
 // fp32 FFMA GEMM (RB200_PREC_FP32) and the tcgen05 GEMM family (all other modes)
 int launch_gemm_simt(const GemmArgs& g, cudaStream_t s);

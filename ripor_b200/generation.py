@@ -138,6 +138,7 @@ def generate_for_constrained_prefix_beam_search(model, valid_smtids, inputs: Opt
     out = BeamSearchEncoderDecoderOutput(seqs, scores, leaf)
     out.gpu_launches = int(L.rb200_engine_last_launch_count(engine.h))
     out.precision = mode
+    out.forced_tail_from = int(L.rb200_engine_last_tail_step(engine.h))   # -1: stepwise to the end
     if return_dict_in_generate is False:
         return seqs
     return out

@@ -316,3 +316,28 @@ def test_t5large_dims_match_cached_oracle():
     model = T5SeqAQEncoder.from_weights(dims, w)
     out = _engine_search(model, DocidTrie.from_codes(codes, V), ids, mask, nb, L, precision="fp16x3")
     assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp16x3"])
+@pytest.mark.parametrize("log_softmax", [False, True])
+def test_forced_tail_equals_step_by_step(monkeypatch, precision, log_softmax):
+    """Once every beam sits on a single trie leaf the engine runs the remaining positions as one teacher-forced pass;
+    the result must be what the step-by-step loop gives (and what the oracle gives)."""
+    L, nb, B = 12, 6, 5
+    dims = syn.T5Dims.tiny(docid_len=L)
+    w = syn.make_weights(dims)
+    V = dims.decoder_vocab_size
+    codes = syn.make_codes(3000, L, V)
+    ids, mask = syn.make_queries(B, S=20, vocab_size=dims.vocab_size)
+    ref_seq, ref_sc, _, _ = helpers.oracle_cached_search(w, dims, codes, ids, mask, nb, L, log_softmax=log_softmax)
+    trie = DocidTrie.from_codes(codes, V)
+    outs = {}
+    for tail in ("1", "0"):
+        monkeypatch.setenv("RB200_TAIL", tail)                      # read when the engine is created
+        model = T5SeqAQEncoder.from_weights(dims, w)
+        outs[tail] = _engine_search(model, trie, ids, mask, nb, L, log_softmax, precision=precision)
+        assert helpers.compare_ranked(outs[tail].sequences, outs[tail].sequences_scores, ref_seq, ref_sc, nb,
+                                      atol=1e-3) == 0
+    assert 1 <= outs["1"].forced_tail_from < L - 1 and outs["0"].forced_tail_from == -1
+    assert torch.equal(outs["1"].sequences, outs["0"].sequences)
+    assert torch.allclose(outs["1"].sequences_scores, outs["0"].sequences_scores, atol=2e-5, rtol=0)
