@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArg
 // Forced tail: all T remaining positions of a beam row in one task. The K/V rows of the whole lineage (cached
 // prefix + the T new positions) are staged once and serve T queries; the lane that owns key position p keeps its K
 // row in registers across the queries.
-constexpr int kTailWarpFloats = 32 * 64 * 3 + 32;          // K | V | q rows of up to 32 positions | exp(scores)
+constexpr int kTailJB = 4;                                  // queries in flight per warp (independent chains)
+constexpr int kTailWarpFloats = 32 * 64 * 3 + kTailJB * 32;   // K | V | q rows of up to 32 positions | exp(scores)
 
 __global__ void __launch_bounds__(kWarps * 32, 2) self_attn_tail_kernel(TailAttnArgs a, ActOut ctx) {
   extern __shared__ __align__(16) float tsmem[];
@@ -277,33 +278,53 @@ __global__ void __launch_bounds__(kWarps * 32, 2) self_attn_tail_kernel(TailAttn
     for (int j = 0; j < 16; ++j)
       k4[j] = lane < P ? *reinterpret_cast<const float4*>(ks + lane * 64 + ((j ^ (lane & 7)) << 2))
                        : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = 0; j < T; ++j) {
-      const int pq = t + j;                                         // position of this query
-      float acc = 0.f;
+    // kTailJB queries at a time: their dot-product, shuffle and accumulate chains are independent, which is what
+    // keeps the few resident warps (shared memory: 2 CTAs per SM) issuing
+    for (int j0 = 0; j0 < T; j0 += kTailJB) {
+      float acc[kTailJB];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc = dot4(*reinterpret_cast<const float4*>(qs + j * 64 + c * 4), k4[c], acc);
-      const float sc = lane <= pq ? acc + __ldg(a.bias + h * L + (pq - lane)) : -INFINITY;
-      const float mx = warp_max(sc);
-      const float e = expf(sc - mx);                                // 0 beyond the query's own position
-      const float sum = warp_sum(e);
+      for (int u = 0; u < kTailJB; ++u) acc[u] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {                                // fully unrolled: k4[] must stay in registers
+#pragma unroll
+        for (int u = 0; u < kTailJB; ++u)
+          acc[u] = dot4(*reinterpret_cast<const float4*>(qs + min(j0 + u, T - 1) * 64 + c * 4), k4[c], acc[u]);
+      }
+      float inv[kTailJB];
+      __syncwarp();                                                 // the previous group's readers of es are done
+#pragma unroll
+      for (int u = 0; u < kTailJB; ++u) {
+        const int pq = t + min(j0 + u, T - 1);                      // position of this query
+        const float sc = lane <= pq ? acc[u] + __ldg(a.bias + h * L + (pq - lane)) : -INFINITY;
+        const float mx = warp_max(sc);
+        const float e = expf(sc - mx);                              // 0 beyond the query's own position
+        inv[u] = 1.0f / warp_sum(e);
+        es[u * 32 + lane] = e;
+      }
       __syncwarp();
-      es[lane] = e;
-      __syncwarp();
-      float2 o2 = make_float2(0.f, 0.f);
-      const int ng = (pq + 4) >> 2;
+      float2 o2[kTailJB];
+#pragma unroll
+      for (int u = 0; u < kTailJB; ++u) o2[u] = make_float2(0.f, 0.f);
+      const int ng = (t + min(j0 + kTailJB - 1, T - 1) + 4) >> 2;   // groups of 4 positions up to the last query's own
       for (int g = 0; g < ng; ++g) {
-        const float4 e4 = *reinterpret_cast<const float4*>(es + 4 * g);
         const float2 v0 = *reinterpret_cast<const float2*>(vs + (4 * g + 0) * 64 + lane * 2);
         const float2 v1 = *reinterpret_cast<const float2*>(vs + (4 * g + 1) * 64 + lane * 2);
         const float2 v2 = *reinterpret_cast<const float2*>(vs + (4 * g + 2) * 64 + lane * 2);
         const float2 v3 = *reinterpret_cast<const float2*>(vs + (4 * g + 3) * 64 + lane * 2);
-        o2.x = fmaf(e4.x, v0.x, o2.x); o2.y = fmaf(e4.x, v0.y, o2.y);
-        o2.x = fmaf(e4.y, v1.x, o2.x); o2.y = fmaf(e4.y, v1.y, o2.y);
-        o2.x = fmaf(e4.z, v2.x, o2.x); o2.y = fmaf(e4.z, v2.y, o2.y);
-        o2.x = fmaf(e4.w, v3.x, o2.x); o2.y = fmaf(e4.w, v3.y, o2.y);
+#pragma unroll
+        for (int u = 0; u < kTailJB; ++u) {
+          const float4 e4 = *reinterpret_cast<const float4*>(es + u * 32 + 4 * g);
+          o2[u].x = fmaf(e4.x, v0.x, o2[u].x); o2[u].y = fmaf(e4.x, v0.y, o2[u].y);
+          o2[u].x = fmaf(e4.y, v1.x, o2[u].x); o2[u].y = fmaf(e4.y, v1.y, o2[u].y);
+          o2[u].x = fmaf(e4.z, v2.x, o2[u].x); o2[u].y = fmaf(e4.z, v2.y, o2[u].y);
+          o2[u].x = fmaf(e4.w, v3.x, o2[u].x); o2[u].y = fmaf(e4.w, v3.y, o2[u].y);
+        }
       }
-      const float inv = 1.0f / sum;
-      act_store2(ctx, ((int64_t)j * R + r) * inner + h * 64 + lane * 2, make_float2(o2.x * inv, o2.y * inv));
+#pragma unroll
+      for (int u = 0; u < kTailJB; ++u)
+        if (j0 + u < T)
+          act_store2(ctx, ((int64_t)(j0 + u) * R + r) * inner + h * 64 + lane * 2,
+                     make_float2(o2[u].x * inv[u], o2[u].y * inv[u]));
     }
   }
   pdl_trigger();
@@ -315,8 +336,16 @@ __global__ void __launch_bounds__(kWarps * 32, 2) self_attn_tail_kernel(TailAttn
 // QS: the beams' q rows are staged in shared memory too; XB: beams (query rows) per warp. Fewer beams per warp =
 // fewer registers and less shared memory per warp, i.e. more resident warps to hide the staging latency, at the
 // price of staging a query's K/V once per group of XB beams (the repeats hit L2).
+
 template <bool QS, int XB>
-constexpr int x_warp_floats() { return 32 * 64 + 32 * 64 + XB * 32 + (QS ? XB * 64 : 0); }   // K | V | exp | q
+constexpr int x_warp_floats() { return 32 * 64 + 32 * 64 + XB * 32 + (QS ? 2 * XB * 64 : 0); }   // K | V | exp | 2 x q
+// ~20 KB of shared memory per warp: ONE CTA per SM with as many warps as fit (9-11) uses the 227 KB better than
+// 2 CTAs x 4 warps
+template <bool QS, int XB>
+constexpr int x_warps() {
+  constexpr int n = (226 * 1024) / (x_warp_floats<QS, XB>() * 4);
+  return n > 12 ? 12 : n;
+}
 
 __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bool on) {
   const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst_smem);
@@ -324,16 +353,17 @@ __device__ __forceinline__ void cp_async16(float* dst_smem, const float* src, bo
 }
 
 template <bool QS, int XB>
-__global__ void __launch_bounds__(kWarps * 32, XB <= 5 ? 3 : 2) cross_attn_warp_kernel(CrossAttnArgs a, ActOut ctx) {
+__global__ void __launch_bounds__(x_warps<QS, XB>() * 32, 1) cross_attn_warp_kernel(CrossAttnArgs a, ActOut ctx) {
   constexpr int kXB = XB;
+  constexpr int kXWarps = x_warps<QS, XB>();
   extern __shared__ __align__(16) float xsmem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;
   float* ks = xsmem + warp * x_warp_floats<QS, XB>();
   float* vs = ks + 32 * 64;                                        // K rows: 16-byte chunks XOR-swizzled by row
   float* es = vs + 32 * 64;
-  float* qs = es + kXB * 32;
-  const int wid = blockIdx.x * kWarps + warp;
+  float* qs = es + kXB * 32;                                       // two buffers of XB rows (QS only)
+  const int wid = blockIdx.x * kXWarps + warp;
   const int b = wid / a.H, h = wid - b * a.H;
   const int rpq = a.rows_per_query, S = a.S;
   pdl_wait();
@@ -341,116 +371,628 @@ __global__ void __launch_bounds__(kWarps * 32, XB <= 5 ? 3 : 2) cross_attn_warp_
   const int inner = a.H * 64;
   const int i0 = blockIdx.y * kXB;
   const int nact = min(kXB, rpq - i0);
-  const int64_t row0 = (int64_t)blockIdx.z * a.block_rows + (int64_t)b * rpq + i0;
   const int64_t* mk = a.mask + (int64_t)b * S;
-  // q rows of this warp's beams -> shared memory (joins the first K commit group); rows beyond nact repeat row 0
   const int64_t q_ld = a.q_ld ? a.q_ld : inner;
-  const float* qg = a.q + row0 * q_ld + h * 64;
-  if (QS) {
-    const float* qb = qg + l16 * 4;
-#pragma unroll
-    for (int r = 0; r < (kXB + 1) / 2; ++r) {
-      const int i = 2 * r + half;
-      if (i < kXB) cp_async16(qs + i * 64 + l16 * 4, qb + (int64_t)(i < nact ? i : 0) * q_ld, true);
-    }
-  }
   // this lane's source pointer for staging: row (half) of the chunk, 16-byte column l16; advances 2 rows per step
   const float* kv_lane = a.kv + ((int64_t)b * S + half) * a.ld + h * 64 + l16 * 4;
   const int64_t step2 = 2 * a.ld;
-
-  float run_max[kXB], run_sum[kXB];
-  float2 o2[kXB];
+  const bool resident = S <= 32;       // one chunk: the staged K/V serve every position block of the forced tail
+  auto row_of = [&](int z) { return (int64_t)z * a.block_rows + (int64_t)b * rpq + i0; };
+  auto stage_q = [&](int z, float* dst) {                          // q rows of block z; rows beyond nact repeat row 0
+    const float* qb = a.q + row_of(z) * q_ld + h * 64 + l16 * 4;
 #pragma unroll
-  for (int i = 0; i < kXB; ++i) { run_max[i] = -INFINITY; run_sum[i] = 0.f; o2[i] = make_float2(0.f, 0.f); }
-
-  for (int c0 = 0; c0 < S; c0 += 32) {
-    const int p = c0 + lane;
-    const bool ok = p < S && mk[p < S ? p : 0] != 0;
-    const unsigned bits = __ballot_sync(0xffffffffu, ok);
-    if (bits == 0) continue;                                       // warp-uniform: a fully masked chunk
-    if (c0 > 0) __syncwarp();                                      // previous chunk's readers are done with ks/vs/es
-    // ---- stage the chunk: 16 lanes x 16 B per row, two rows per instruction, zero fill for masked keys ---------
-    {
-      const float* src = kv_lane + (int64_t)c0 * a.ld + a.k_off;
-      const unsigned mybits = bits >> half;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const bool on = (mybits >> (2 * r)) & 1u;
-        cp_async16(ks + (2 * r + half) * 64 + ((l16 ^ ((2 * r + half) & 7)) << 2), on ? src : a.kv, on);
-        src += step2;
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
-      src = kv_lane + (int64_t)c0 * a.ld + a.v_off;
-#pragma unroll
-      for (int r = 0; r < 16; ++r) {
-        const bool on = (mybits >> (2 * r)) & 1u;
-        cp_async16(vs + (2 * r + half) * 64 + l16 * 4, on ? src : a.kv, on);
-        src += step2;
-      }
-      asm volatile("cp.async.commit_group;" ::: "memory");
+    for (int r = 0; r < (kXB + 1) / 2; ++r) {
+      const int i = 2 * r + half;
+      if (i < kXB) cp_async16(dst + i * 64 + l16 * 4, qb + (int64_t)(i < nact ? i : 0) * q_ld, true);
     }
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    // ---- scores: lane = key; the K row comes from shared memory once and meets every beam's q -----------------
-    float sc[kXB];
+  };
+  const int z0 = blockIdx.z, zs = gridDim.z;
+  if (QS) stage_q(z0, qs);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  int qbuf = 0;
+  for (int z = z0; z < a.nblocks; z += zs, qbuf ^= 1) {
+    const int64_t row0 = row_of(z);
+    const float* qcur = qs + qbuf * (kXB * 64);
+    const float* qg = a.q + row0 * q_ld + h * 64;
+    __syncwarp();                                                  // the previous block's readers are done
+    if (QS && z + zs < a.nblocks) stage_q(z + zs, qs + (qbuf ^ 1) * (kXB * 64));   // prefetch the next block's q
+    asm volatile("cp.async.commit_group;" ::: "memory");           // (possibly empty: uniform group accounting)
+    float run_max[kXB], run_sum[kXB];
+    float2 o2[kXB];
 #pragma unroll
-    for (int i = 0; i < kXB; ++i) sc[i] = 0.f;
+    for (int i = 0; i < kXB; ++i) { run_max[i] = -INFINITY; run_sum[i] = 0.f; o2[i] = make_float2(0.f, 0.f); }
+    for (int c0 = 0; c0 < S; c0 += 32) {
+      const int p = c0 + lane;
+      const bool ok = p < S && mk[p < S ? p : 0] != 0;
+      const unsigned bits = __ballot_sync(0xffffffffu, ok);
+      if (bits == 0) continue;                                     // warp-uniform: a fully masked chunk
+      const bool stage_now = !(resident && z > z0);
+      if (stage_now) {
+        if (c0 > 0) __syncwarp();                                  // previous chunk's readers are done with ks/vs/es
+        // ---- stage the chunk: 16 lanes x 16 B per row, two rows per instruction, zero fill for masked keys -------
+        const float* src = kv_lane + (int64_t)c0 * a.ld + a.k_off;
+        const unsigned mybits = bits >> half;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const bool on = (mybits >> (2 * r)) & 1u;
+          cp_async16(ks + (2 * r + half) * 64 + ((l16 ^ ((2 * r + half) & 7)) << 2), on ? src : a.kv, on);
+          src += step2;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        src = kv_lane + (int64_t)c0 * a.ld + a.v_off;
+#pragma unroll
+        for (int r = 0; r < 16; ++r) {
+          const bool on = (mybits >> (2 * r)) & 1u;
+          cp_async16(vs + (2 * r + half) * 64 + l16 * 4, on ? src : a.kv, on);
+          src += step2;
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+      }
+      asm volatile("cp.async.wait_group 1;" ::: "memory");         // everything but the newest group (V, or next q)
+      __syncwarp();
+      // ---- scores: lane = key; the K row comes from shared memory once and meets every beam's q ---------------
+      float sc[kXB];
+#pragma unroll
+      for (int i = 0; i < kXB; ++i) sc[i] = 0.f;
 #pragma unroll 4
-    for (int j = 0; j < 16; ++j) {
-      const float4 k4 = *reinterpret_cast<const float4*>(ks + lane * 64 + ((j ^ (lane & 7)) << 2));
+      for (int j = 0; j < 16; ++j) {
+        const float4 k4 = *reinterpret_cast<const float4*>(ks + lane * 64 + ((j ^ (lane & 7)) << 2));
+#pragma unroll
+        for (int i = 0; i < kXB; ++i) {
+          const float4 q4 = QS ? *reinterpret_cast<const float4*>(qcur + i * 64 + j * 4)
+                               : __ldg(reinterpret_cast<const float4*>(qg + (int64_t)(i < nact ? i : 0) * q_ld) + j);
+          sc[i] = dot4(q4, k4, sc[i]);
+        }
+      }
+      if (a.rel_bias != nullptr && ok) {   // encoder: query row i0 + i of the sequence, key p
+        const float* rb_h = a.rel_bias + (int64_t)h * (2 * S - 1) + (p + S - 1 - i0);
+#pragma unroll
+        for (int i = 0; i < kXB; ++i)
+          if (i < nact) sc[i] += __ldg(rb_h - i);
+      }
+      if (!stage_now) __syncwarp();                                // es of the previous block has been consumed
 #pragma unroll
       for (int i = 0; i < kXB; ++i) {
-        const float4 q4 = QS ? *reinterpret_cast<const float4*>(qs + i * 64 + j * 4)
-                             : __ldg(reinterpret_cast<const float4*>(qg + (int64_t)(i < nact ? i : 0) * q_ld) + j);
-        sc[i] = dot4(q4, k4, sc[i]);
+        const float s_i = ok ? sc[i] : -INFINITY;
+        const float new_max = fmaxf(run_max[i], warp_max(s_i));    // finite: the chunk has an unmasked key
+        const float rescale = expf(run_max[i] - new_max);
+        const float e = expf(s_i - new_max);                       // 0 for masked keys
+        run_max[i] = new_max;
+        run_sum[i] = run_sum[i] * rescale + warp_sum(e);
+        o2[i].x *= rescale;
+        o2[i].y *= rescale;
+        es[i * 32 + lane] = e;
+      }
+      if (stage_now) asm volatile("cp.async.wait_group 0;" ::: "memory");   // V (and the prefetched q) landed
+      __syncwarp();
+      // ---- context: lane = a pair of output dims; 4 keys per iteration from shared memory ----------------------
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        if (((bits >> (4 * g)) & 0xFu) == 0) continue;             // warp-uniform
+        const float2 v0 = *reinterpret_cast<const float2*>(vs + (4 * g + 0) * 64 + lane * 2);
+        const float2 v1 = *reinterpret_cast<const float2*>(vs + (4 * g + 1) * 64 + lane * 2);
+        const float2 v2 = *reinterpret_cast<const float2*>(vs + (4 * g + 2) * 64 + lane * 2);
+        const float2 v3 = *reinterpret_cast<const float2*>(vs + (4 * g + 3) * 64 + lane * 2);
+#pragma unroll
+        for (int i = 0; i < kXB; ++i) {
+          const float4 e4 = *reinterpret_cast<const float4*>(es + i * 32 + 4 * g);
+          o2[i].x = fmaf(e4.x, v0.x, o2[i].x); o2[i].y = fmaf(e4.x, v0.y, o2[i].y);
+          o2[i].x = fmaf(e4.y, v1.x, o2[i].x); o2[i].y = fmaf(e4.y, v1.y, o2[i].y);
+          o2[i].x = fmaf(e4.z, v2.x, o2[i].x); o2[i].y = fmaf(e4.z, v2.y, o2[i].y);
+          o2[i].x = fmaf(e4.w, v3.x, o2[i].x); o2[i].y = fmaf(e4.w, v3.y, o2[i].y);
+        }
       }
     }
-    if (a.rel_bias != nullptr && ok) {   // encoder: query row i0 + i of the sequence, key p
-      const float* rb_h = a.rel_bias + (int64_t)h * (2 * S - 1) + (p + S - 1 - i0);
 #pragma unroll
-      for (int i = 0; i < kXB; ++i)
-        if (i < nact) sc[i] += __ldg(rb_h - i);
-    }
-#pragma unroll
-    for (int i = 0; i < kXB; ++i) {
-      const float s_i = ok ? sc[i] : -INFINITY;
-      const float new_max = fmaxf(run_max[i], warp_max(s_i));      // finite: the chunk has an unmasked key
-      const float rescale = expf(run_max[i] - new_max);
-      const float e = expf(s_i - new_max);                         // 0 for masked keys
-      run_max[i] = new_max;
-      run_sum[i] = run_sum[i] * rescale + warp_sum(e);
-      o2[i].x *= rescale;
-      o2[i].y *= rescale;
-      es[i * 32 + lane] = e;
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();
-    // ---- context: lane = a pair of output dims; 4 keys per iteration from shared memory ------------------------
-#pragma unroll
-    for (int g = 0; g < 8; ++g) {
-      if (((bits >> (4 * g)) & 0xFu) == 0) continue;               // warp-uniform
-      const float2 v0 = *reinterpret_cast<const float2*>(vs + (4 * g + 0) * 64 + lane * 2);
-      const float2 v1 = *reinterpret_cast<const float2*>(vs + (4 * g + 1) * 64 + lane * 2);
-      const float2 v2 = *reinterpret_cast<const float2*>(vs + (4 * g + 2) * 64 + lane * 2);
-      const float2 v3 = *reinterpret_cast<const float2*>(vs + (4 * g + 3) * 64 + lane * 2);
-#pragma unroll
-      for (int i = 0; i < kXB; ++i) {
-        const float4 e4 = *reinterpret_cast<const float4*>(es + i * 32 + 4 * g);
-        o2[i].x = fmaf(e4.x, v0.x, o2[i].x); o2[i].y = fmaf(e4.x, v0.y, o2[i].y);
-        o2[i].x = fmaf(e4.y, v1.x, o2[i].x); o2[i].y = fmaf(e4.y, v1.y, o2[i].y);
-        o2[i].x = fmaf(e4.z, v2.x, o2[i].x); o2[i].y = fmaf(e4.z, v2.y, o2[i].y);
-        o2[i].x = fmaf(e4.w, v3.x, o2[i].x); o2[i].y = fmaf(e4.w, v3.y, o2[i].y);
+    for (int i = 0; i < kXB; ++i)
+      if (i < nact) {
+        const float inv = run_sum[i] > 0.f ? 1.0f / run_sum[i] : 0.f;
+        act_store2(ctx, (row0 + i) * inner + h * 64 + lane * 2, make_float2(o2[i].x * inv, o2[i].y * inv));
       }
+  }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");             // (a fully masked query never waited for its q rows)
+  pdl_trigger();
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// forced tail, cross-attention on the (legacy) warp-level tensor cores
+// ------------------------------------------------------------------------------------------------------------
+// In the forced tail every (query, head) pair serves T * nb rows (280 at the bench shape) against the same <= 32
+// keys, which makes it a small GEMM pair: S = Q K^T (rows x 32 keys over 64 dims), O = softmax(S) V. The FFMA kernel
+// above is issue-bound there (1440 warp instructions per 5 rows). This kernel runs 16-row tiles through
+// mma.sync.m16n8k8 tf32 with the same error-compensated 3-product split as the GEMMs (hi*hi + hi*lo + lo*hi, fp32
+// accumulate), so the scores keep fp32-grade accuracy. K and V are split once per CTA into shared memory.
+constexpr int kMmaLd = 68;   // row stride (floats) of the staged K/V planes: conflict-free fragment reads
+
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const float (&a)[4], float b0, float b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(__float_as_uint(a[0])), "r"(__float_as_uint(a[1])), "r"(__float_as_uint(a[2])), "r"(__float_as_uint(a[3])),
+        "r"(__float_as_uint(b0)), "r"(__float_as_uint(b1)));
+}
+
+__global__ void __launch_bounds__(128, 3) cross_attn_mma_kernel(CrossAttnArgs a, ActOut ctx) {
+  __shared__ __align__(16) float k_hi[32 * kMmaLd], k_lo[32 * kMmaLd], v_hi[32 * kMmaLd], v_lo[32 * kMmaLd];
+  __shared__ unsigned valid_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.x / a.H, h = blockIdx.x - b * a.H;
+  const int S = a.S, rpq = a.rows_per_query, inner = a.H * 64;
+  pdl_wait();
+  // ---- K, V of this (query, head): split into tf32 planes once; masked / absent keys are zero rows --------------
+  const int64_t* mk = a.mask + (int64_t)b * S;
+  if (warp == 0) {
+    const bool ok = lane < S && mk[lane < S ? lane : 0] != 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) valid_s = bits;
+  }
+  __syncthreads();
+  const unsigned valid = valid_s;
+  const float* kvb = a.kv + (int64_t)b * S * a.ld + h * 64;
+  for (int e = threadIdx.x; e < 32 * 16; e += blockDim.x) {
+    const int key = e >> 4, c4 = (e & 15) * 4;
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+    if ((valid >> key) & 1u) {
+      kk = __ldg(reinterpret_cast<const float4*>(kvb + (int64_t)key * a.ld + a.k_off + c4));
+      vv = __ldg(reinterpret_cast<const float4*>(kvb + (int64_t)key * a.ld + a.v_off + c4));
+    }
+    const float kf[4] = {kk.x, kk.y, kk.z, kk.w}, vf[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float kh = round_tf32(kf[u]), vh = round_tf32(vf[u]);
+      k_hi[key * kMmaLd + c4 + u] = kh;
+      k_lo[key * kMmaLd + c4 + u] = round_tf32(kf[u] - kh);
+      v_hi[key * kMmaLd + c4 + u] = vh;
+      v_lo[key * kMmaLd + c4 + u] = round_tf32(vf[u] - vh);
+    }
+  }
+  __syncthreads();
+  // ---- 16-row tiles of this query's rows: tile row q <-> (position block q / rpq, beam q % rpq) ------------------
+  const int nrows = a.nblocks * rpq;
+  const int64_t q_ld = a.q_ld ? a.q_ld : inner;
+  auto global_row = [&](int q) { return (int64_t)(q / rpq) * a.block_rows + (int64_t)b * rpq + (q % rpq); };
+  for (int tile = warp; tile * 16 < nrows; tile += 4) {
+    const int q0 = tile * 16 + g, q1 = q0 + 8;                      // this lane's two rows of the tile
+    const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64;
+    const float* qr1 = a.q + global_row(min(q1, nrows - 1)) * q_ld + h * 64;
+    float qa[8][4];                                                 // A fragments of the 8 k-steps (raw fp32)
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      qa[kk][0] = __ldg(qr0 + kk * 8 + t);
+      qa[kk][1] = __ldg(qr1 + kk * 8 + t);
+      qa[kk][2] = __ldg(qr0 + kk * 8 + t + 4);
+      qa[kk][3] = __ldg(qr1 + kk * 8 + t + 4);
+    }
+    // S = Q K^T: 4 key tiles of 8
+    float sacc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sacc[nt][u] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 8; ++kk) {
+      float ah[4], al[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ah[u] = round_tf32(qa[kk][u]);
+        al[u] = round_tf32(qa[kk][u] - ah[u]);
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int o0 = (nt * 8 + g) * kMmaLd + kk * 8 + t;          // B(k = t, n = g) = K[key nt*8+g][dim kk*8+t]
+        const float bh0 = k_hi[o0], bh1 = k_hi[o0 + 4], bl0 = k_lo[o0], bl1 = k_lo[o0 + 4];
+        mma_tf32(sacc[nt], al, bh0, bh1);
+        mma_tf32(sacc[nt], ah, bl0, bl1);
+        mma_tf32(sacc[nt], ah, bh0, bh1);
+      }
+    }
+    // softmax over the keys of rows q0 (c0, c1) and q1 (c2, c3); key of c(2u'+w) in tile nt = nt*8 + 2t + w
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const bool on = (valid >> (nt * 8 + 2 * t + w)) & 1u;
+        sacc[nt][w] = on ? sacc[nt][w] : -INFINITY;
+        sacc[nt][2 + w] = on ? sacc[nt][2 + w] : -INFINITY;
+        mx0 = fmaxf(mx0, sacc[nt][w]);
+        mx1 = fmaxf(mx1, sacc[nt][2 + w]);
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        sacc[nt][w] = mx0 == -INFINITY ? 0.f : expf(sacc[nt][w] - mx0);
+        sacc[nt][2 + w] = mx1 == -INFINITY ? 0.f : expf(sacc[nt][2 + w] - mx1);
+        sum0 += sacc[nt][w];
+        sum1 += sacc[nt][2 + w];
+      }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // O = P V. The C fragment of key tile ks IS an A fragment if A's column c stands for key 2c (c < 4) / 2(c-4)+1:
+    // a0 = c0, a1 = c2, a2 = c1, a3 = c3; the V rows of the B fragment follow the same key order.
+    float oacc[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) oacc[nd][u] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) {
+      const float pf[4] = {sacc[ks][0], sacc[ks][2], sacc[ks][1], sacc[ks][3]};
+      float ph[4], pl[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        ph[u] = round_tf32(pf[u]);
+        pl[u] = round_tf32(pf[u] - ph[u]);
+      }
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd) {
+        const int o0 = (ks * 8 + 2 * t) * kMmaLd + nd * 8 + g;       // B(k = t, n = g) = V[key ks*8+2t][dim nd*8+g]
+        const float bh0 = v_hi[o0], bh1 = v_hi[o0 + kMmaLd], bl0 = v_lo[o0], bl1 = v_lo[o0 + kMmaLd];
+        mma_tf32(oacc[nd], pl, bh0, bh1);
+        mma_tf32(oacc[nd], ph, bl0, bl1);
+        mma_tf32(oacc[nd], ph, bh0, bh1);
+      }
+    }
+    const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
+    if (q0 < nrows) {
+      const int64_t base = global_row(q0) * inner + h * 64 + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
+    }
+    if (q1 < nrows) {
+      const int64_t base = global_row(q1) * inner + h * 64 + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
     }
   }
   pdl_trigger();
-  asm volatile("cp.async.wait_group 0;" ::: "memory");             // (a fully masked query never waited for its q rows)
-#pragma unroll
-  for (int i = 0; i < kXB; ++i)
-    if (i < nact) {
-      const float inv = run_sum[i] > 0.f ? 1.0f / run_sum[i] : 0.f;
-      act_store2(ctx, (row0 + i) * inner + h * 64 + lane * 2, make_float2(o2[i].x * inv, o2[i].y * inv));
+}
+
+// fp16x3 flavour of the tensor-core cross-attention (precision mode fp16x3 only): the operands are split into two
+// fp16 planes like the GEMM operands of that mode (11-bit mantissas, range-checked), which lets m16n8k16 do twice the
+// contraction per instruction and halves the fragment traffic. K and V are staged row-major as fp16 planes; the V
+// fragments of P V come out of ldmatrix.trans.
+constexpr int kKLd = 72;   // halfs per staged K row (64 dims + pad): conflict-free B fragments
+
+__device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// four transposed 8x8 b16 matrices: with V kept row-major [key][dim], lane l passes the address of row
+// (key0 + (l & 7) + 8 * ((l >> 3) & 1)) at dim0 + 8 * (l >> 4) and receives b0, b1 of dim tile 0 and b0, b1 of dim tile 1
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const __half* row_ptr) {
+  const uint32_t addr = (uint32_t)__cvta_generic_to_shared(row_ptr);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+// (x, y) -> fp16 pair hi and the fp16 pair of the remainders; flags values outside the fp16 range
+__device__ __forceinline__ void split_h2(float x, float y, uint32_t& hi, uint32_t& lo, bool& bad) {
+  bad |= !(fabsf(x) <= kFp16Limit && fabsf(y) <= kFp16Limit);
+  const __half2 h = __floats2half2_rn(x, y);
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(x - hf.x, y - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+
+__global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs a, ActOut ctx) {
+  __shared__ __align__(16) __half k_hi[32 * kKLd], k_lo[32 * kKLd], v_hi[32 * kKLd], v_lo[32 * kKLd];
+  __shared__ unsigned valid_s;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int b = blockIdx.x / a.H, h = blockIdx.x - b * a.H;
+  const int S = a.S, rpq = a.rows_per_query, inner = a.H * 64;
+  bool bad = false;
+  pdl_wait();
+  const int64_t* mk = a.mask + (int64_t)b * S;
+  if (warp == 0) {
+    const bool ok = lane < S && mk[lane < S ? lane : 0] != 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, ok);
+    if (lane == 0) valid_s = bits;
+  }
+  __syncthreads();
+  const unsigned valid = valid_s;
+  const float* kvb = a.kv + (int64_t)b * S * a.ld + h * 64;
+  for (int e = threadIdx.x; e < 32 * 16; e += blockDim.x) {
+    const int key = e >> 4, c4 = (e & 15) * 4;
+    float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+    if ((valid >> key) & 1u) {
+      kk = __ldg(reinterpret_cast<const float4*>(kvb + (int64_t)key * a.ld + a.k_off + c4));
+      vv = __ldg(reinterpret_cast<const float4*>(kvb + (int64_t)key * a.ld + a.v_off + c4));
     }
+    uint32_t h0, l0, h1, l1;
+    split_h2(kk.x, kk.y, h0, l0, bad);
+    split_h2(kk.z, kk.w, h1, l1, bad);
+    *reinterpret_cast<uint2*>(k_hi + key * kKLd + c4) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(k_lo + key * kKLd + c4) = make_uint2(l0, l1);
+    split_h2(vv.x, vv.y, h0, l0, bad);
+    split_h2(vv.z, vv.w, h1, l1, bad);
+    *reinterpret_cast<uint2*>(v_hi + key * kKLd + c4) = make_uint2(h0, h1);
+    *reinterpret_cast<uint2*>(v_lo + key * kKLd + c4) = make_uint2(l0, l1);
+  }
+  __syncthreads();
+  const int nrows = a.nblocks * rpq;
+  const int64_t q_ld = a.q_ld ? a.q_ld : inner;
+  auto global_row = [&](int q) { return (int64_t)(q / rpq) * a.block_rows + (int64_t)b * rpq + (q % rpq); };
+  const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
+  const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
+  const int vrow = (lane & 7) + 8 * ((lane >> 3) & 1), vcol = 8 * (lane >> 4);   // ldmatrix row of this lane
+  for (int tile = warp; tile * 16 < nrows; tile += 4) {
+    const int q0 = tile * 16 + g, q1 = q0 + 8;
+    const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64 + 2 * t;
+    const float* qr1 = a.q + global_row(min(q1, nrows - 1)) * q_ld + h * 64 + 2 * t;
+    float2 qa[4][4];                                                // A fragments (raw fp32 pairs) of the 4 k-steps
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      qa[kk][0] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16));
+      qa[kk][1] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16));
+      qa[kk][2] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16 + 8));
+      qa[kk][3] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16 + 8));
+    }
+    float sacc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sacc[nt][u] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      uint32_t ah[4], al[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) split_h2(qa[kk][u].x, qa[kk][u].y, ah[u], al[u], bad);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t;      // words: K[key nt*8+g][dims kk*16 + 2t, +1]
+        const uint32_t bh0 = kh32[o0], bh1 = kh32[o0 + 4], bl0 = kl32[o0], bl1 = kl32[o0 + 4];
+        mma_f16(sacc[nt], al, bh0, bh1);
+        mma_f16(sacc[nt], ah, bl0, bl1);
+        mma_f16(sacc[nt], ah, bh0, bh1);
+      }
+    }
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const bool on = (valid >> (nt * 8 + 2 * t + w)) & 1u;
+        sacc[nt][w] = on ? sacc[nt][w] : -INFINITY;
+        sacc[nt][2 + w] = on ? sacc[nt][2 + w] : -INFINITY;
+        mx0 = fmaxf(mx0, sacc[nt][w]);
+        mx1 = fmaxf(mx1, sacc[nt][2 + w]);
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        sacc[nt][w] = mx0 == -INFINITY ? 0.f : expf(sacc[nt][w] - mx0);
+        sacc[nt][2 + w] = mx1 == -INFINITY ? 0.f : expf(sacc[nt][2 + w] - mx1);
+        sum0 += sacc[nt][w];
+        sum1 += sacc[nt][2 + w];
+      }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    // O = P V: the C fragments of key tiles 2ks and 2ks+1 are exactly the A fragment of 16-key step ks
+    float oacc[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) oacc[nd][u] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t ph[4], pl[4];
+      bool nb_ = false;                                             // probabilities are in [0, 1]
+      split_h2(sacc[2 * ks][0], sacc[2 * ks][1], ph[0], pl[0], nb_);
+      split_h2(sacc[2 * ks][2], sacc[2 * ks][3], ph[1], pl[1], nb_);
+      split_h2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ph[2], pl[2], nb_);
+      split_h2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ph[3], pl[3], nb_);
+#pragma unroll
+      for (int nd = 0; nd < 8; nd += 2) {
+        uint32_t bh[4], bl[4];                                     // b0, b1 of dim tiles nd and nd + 1
+        ldmatrix_x4_trans(bh, v_hi + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
+        ldmatrix_x4_trans(bl, v_lo + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
+        mma_f16(oacc[nd], pl, bh[0], bh[1]);
+        mma_f16(oacc[nd], ph, bl[0], bl[1]);
+        mma_f16(oacc[nd], ph, bh[0], bh[1]);
+        mma_f16(oacc[nd + 1], pl, bh[2], bh[3]);
+        mma_f16(oacc[nd + 1], ph, bl[2], bl[3]);
+        mma_f16(oacc[nd + 1], ph, bh[2], bh[3]);
+      }
+    }
+    const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
+    if (q0 < nrows) {
+      const int64_t base = global_row(q0) * inner + h * 64 + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
+    }
+    if (q1 < nrows) {
+      const int64_t base = global_row(q1) * inner + h * 64 + 2 * t;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
+    }
+  }
+  if (bad && ctx.overflow) *ctx.overflow = 1;
+  pdl_trigger();
+}
+
+// Forced tail self-attention on the warp-level tensor cores (fp16x3 mode): one warp per (row, head); the lineage's
+// K/V (cached prefix through the ancestry table + the T new positions) are split into fp16 planes in the warp's
+// shared memory once (V transposed), then the T queries run as two 16-row m16n8k16 tiles with the causal mask and
+// the relative position bias applied to the score fragments.
+constexpr int kTailMmaWarpBytes = 4 * 32 * kKLd * 2;          // K hi | K lo | V hi | V lo
+
+__global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(TailAttnArgs a, ActOut ctx) {
+  extern __shared__ __align__(16) unsigned char tmsmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3, half = lane >> 4, l16 = lane & 15;
+  __half* k_hi = reinterpret_cast<__half*>(tmsmem + warp * kTailMmaWarpBytes);
+  __half* k_lo = k_hi + 32 * kKLd;
+  __half* v_hi = k_lo + 32 * kKLd;
+  __half* v_lo = v_hi + 32 * kKLd;
+  const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
+  const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
+  const int vrow = (lane & 7) + 8 * ((lane >> 3) & 1), vcol = 8 * (lane >> 4);   // ldmatrix row of this lane
+  const int inner = a.H * 64, t = a.t, T = a.T, L = a.L, R = a.R;
+  const int P = t + T;
+  const int ntask = R * a.H;
+  bool bad = false;
+  pdl_wait();
+  for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += gridDim.x * kWarps) {
+    const int r = wid / a.H, h = wid - r * a.H;
+    __syncwarp();                                                   // the previous task's fragment reads are done
+    // ---- stage and split K, V of positions 0..P-1 (rows >= P: zeros) -------------------------------------------
+    const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int p = 2 * it + half;
+      const int slot = __shfl_sync(0xffffffffu, slot_l, p);
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (p < P) {
+        if (p < t) {
+          kk = *reinterpret_cast<const float4*>(a.cache_k + (int64_t)slot * inner + h * 64 + l16 * 4);
+          vv = *reinterpret_cast<const float4*>(a.cache_v + (int64_t)slot * inner + h * 64 + l16 * 4);
+        } else {
+          const float* row = a.qkv + ((int64_t)(p - t) * R + r) * 3 * inner + h * 64 + l16 * 4;
+          kk = *reinterpret_cast<const float4*>(row + inner);
+          vv = *reinterpret_cast<const float4*>(row + 2 * inner);
+        }
+      }
+      uint32_t h0, l0, h1, l1;
+      split_h2(kk.x, kk.y, h0, l0, bad);
+      split_h2(kk.z, kk.w, h1, l1, bad);
+      *reinterpret_cast<uint2*>(k_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(k_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
+      split_h2(vv.x, vv.y, h0, l0, bad);
+      split_h2(vv.z, vv.w, h1, l1, bad);
+      *reinterpret_cast<uint2*>(v_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(v_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
+    }
+    __syncwarp();
+    // ---- the T queries as 16-row tiles: tile row q = query index (position t + q) --------------------------------
+    for (int tile = 0; tile * 16 < T; ++tile) {
+      const int q0 = tile * 16 + g, q1 = q0 + 8;
+      const float* qr0 = a.qkv + ((int64_t)min(q0, T - 1) * R + r) * 3 * inner + h * 64 + 2 * t4;
+      const float* qr1 = a.qkv + ((int64_t)min(q1, T - 1) * R + r) * 3 * inner + h * 64 + 2 * t4;
+      float sacc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) sacc[nt][u] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float2 x0 = *reinterpret_cast<const float2*>(qr0 + kk * 16), x1 = *reinterpret_cast<const float2*>(qr1 + kk * 16);
+        const float2 x2 = *reinterpret_cast<const float2*>(qr0 + kk * 16 + 8);
+        const float2 x3 = *reinterpret_cast<const float2*>(qr1 + kk * 16 + 8);
+        uint32_t ah[4], al[4];
+        split_h2(x0.x, x0.y, ah[0], al[0], bad);
+        split_h2(x1.x, x1.y, ah[1], al[1], bad);
+        split_h2(x2.x, x2.y, ah[2], al[2], bad);
+        split_h2(x3.x, x3.y, ah[3], al[3], bad);
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) {
+          const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t4;
+          const uint32_t bh0 = kh32[o0], bh1 = kh32[o0 + 4], bl0 = kl32[o0], bl1 = kl32[o0 + 4];
+          mma_f16(sacc[nt], al, bh0, bh1);
+          mma_f16(sacc[nt], ah, bl0, bl1);
+          mma_f16(sacc[nt], ah, bh0, bh1);
+        }
+      }
+      // causal mask + relative position bias: row q sits at position t + q and sees keys p <= t + q
+      const int pq0 = t + q0, pq1 = t + q1;
+      const float* bias_h = a.bias + h * L;
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int p = nt * 8 + 2 * t4 + w;
+          sacc[nt][w] = (p <= pq0 && q0 < T) ? sacc[nt][w] + __ldg(bias_h + (pq0 - p)) : -INFINITY;
+          sacc[nt][2 + w] = (p <= pq1 && q1 < T) ? sacc[nt][2 + w] + __ldg(bias_h + (pq1 - p)) : -INFINITY;
+          mx0 = fmaxf(mx0, sacc[nt][w]);
+          mx1 = fmaxf(mx1, sacc[nt][2 + w]);
+        }
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          sacc[nt][w] = mx0 == -INFINITY ? 0.f : expf(sacc[nt][w] - mx0);
+          sacc[nt][2 + w] = mx1 == -INFINITY ? 0.f : expf(sacc[nt][2 + w] - mx1);
+          sum0 += sacc[nt][w];
+          sum1 += sacc[nt][2 + w];
+        }
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+      float oacc[8][4];
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) oacc[nd][u] = 0.f;
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks) {
+        uint32_t ph[4], pl[4];
+        bool nb_ = false;
+        split_h2(sacc[2 * ks][0], sacc[2 * ks][1], ph[0], pl[0], nb_);
+        split_h2(sacc[2 * ks][2], sacc[2 * ks][3], ph[1], pl[1], nb_);
+        split_h2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ph[2], pl[2], nb_);
+        split_h2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ph[3], pl[3], nb_);
+#pragma unroll
+        for (int nd = 0; nd < 8; nd += 2) {
+          uint32_t bh[4], bl[4];
+          ldmatrix_x4_trans(bh, v_hi + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
+          ldmatrix_x4_trans(bl, v_lo + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
+          mma_f16(oacc[nd], pl, bh[0], bh[1]);
+          mma_f16(oacc[nd], ph, bl[0], bl[1]);
+          mma_f16(oacc[nd], ph, bh[0], bh[1]);
+          mma_f16(oacc[nd + 1], pl, bh[2], bh[3]);
+          mma_f16(oacc[nd + 1], ph, bl[2], bl[3]);
+          mma_f16(oacc[nd + 1], ph, bh[2], bh[3]);
+        }
+      }
+      const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
+      if (q0 < T) {
+        const int64_t base = ((int64_t)q0 * R + r) * inner + h * 64 + 2 * t4;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd)
+          act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
+      }
+      if (q1 < T) {
+        const int64_t base = ((int64_t)q1 * R + r) * inner + h * 64 + 2 * t4;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd)
+          act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
+      }
+    }
+  }
+  if (bad && ctx.overflow) *ctx.overflow = 1;
+  pdl_trigger();
 }
 
 }  // namespace
@@ -499,8 +1041,13 @@ bool launch_self_attn_warp(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s, in
 template <bool QS, int XB>
 static cudaError_t launch_cross_cfg(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s) {
   const int B = a.M / a.rows_per_query;
-  const dim3 grid(ceil_div((int64_t)B * a.H, kWarps), ceil_div(a.rows_per_query, XB), a.nblocks), block(kWarps * 32);
-  constexpr size_t smem = (size_t)kWarps * x_warp_floats<QS, XB>() * sizeof(float);
+  // position blocks of the forced tail: walked inside the kernel when the staged K/V can stay resident (S <= 32),
+  // one grid slice per block otherwise
+  constexpr int kXWarps = x_warps<QS, XB>();
+  const dim3 grid(ceil_div((int64_t)B * a.H, kXWarps), ceil_div(a.rows_per_query, XB), a.S <= 32 ? 1 : a.nblocks),
+      block(kXWarps * 32);
+  constexpr size_t smem = (size_t)kXWarps * x_warp_floats<QS, XB>() * sizeof(float);
+  static_assert(smem <= 227 * 1024, "cross-attention staging exceeds the shared memory of an SM");
   auto kern = cross_attn_warp_kernel<QS, XB>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -513,24 +1060,49 @@ static cudaError_t launch_cross_cfg(const CrossAttnArgs& a, ActOut ctx, cudaStre
 
 int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s) {
   RB_REQUIRE(a.t >= 1 && a.T >= 1 && a.t + a.T <= 32, "forced tail needs 1 <= t and t + T <= 32 (t=%d, T=%d)", a.t, a.T);
-  constexpr size_t smem = (size_t)kWarps * kTailWarpFloats * sizeof(float);
+  static const bool use_mma = []() {
+    const char* e = getenv("RB200_SELF_MMA");
+    return !(e && e[0] == '0');
+  }();
+  const bool mma = use_mma && prec_is_fp16(ctx.mode);      // tensor-core kernel on fp16 planes; FFMA kernel otherwise
+  const size_t smem = mma ? (size_t)kWarps * kTailMmaWarpBytes : (size_t)kWarps * kTailWarpFloats * sizeof(float);
   static bool attr_set = false;
   static int sms = 0;
   if (!attr_set) {
-    RB_CUDA(cudaFuncSetAttribute(self_attn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    RB_CUDA(cudaFuncSetAttribute(self_attn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)kWarps * kTailWarpFloats * sizeof(float))));
+    RB_CUDA(cudaFuncSetAttribute(self_attn_tail_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)((size_t)kWarps * kTailMmaWarpBytes)));
     int dev = 0;
     RB_CUDA(cudaGetDevice(&dev));
     RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
   const int want = ceil_div((int64_t)a.R * a.H, kWarps);
-  const dim3 grid(want < 2 * sms ? want : 2 * sms), block(kWarps * 32);
-  RB_CUDA(launch_pdl(self_attn_tail_kernel, grid, block, smem, s, a, ctx));
+  const int per_sm = mma ? 3 : 2;
+  const dim3 grid(want < per_sm * sms ? want : per_sm * sms), block(kWarps * 32);
+  if (mma) RB_CUDA(launch_pdl(self_attn_tail_mma16_kernel, grid, block, smem, s, a, ctx));
+  else RB_CUDA(launch_pdl(self_attn_tail_kernel, grid, block, smem, s, a, ctx));
   launch_count()++;
   return 0;
 }
 
 bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, int* status) {
+  static const bool use_mma = []() {
+    const char* e = getenv("RB200_XATTN_MMA");
+    return !(e && e[0] == '0');
+  }();
+  // many rows per (query, head) against <= 32 keys (the forced tail): tensor-core kernel
+  // (the exact fp32 mode keeps the FFMA kernel)
+  if (use_mma && ctx.mode != 0 && a.S <= 32 && a.rel_bias == nullptr && (int64_t)a.nblocks * a.rows_per_query >= 32) {
+    const int B = a.M / a.rows_per_query;
+    const cudaError_t err = prec_is_fp16(ctx.mode)
+                                ? launch_pdl(cross_attn_mma16_kernel, dim3(B * a.H), dim3(128), 0, s, a, ctx)
+                                : launch_pdl(cross_attn_mma_kernel, dim3(B * a.H), dim3(128), 0, s, a, ctx);
+    *status = err == cudaSuccess ? 0 : fail(RB200_ERR_CUDA, "cross_attn_mma_kernel launch: %s", cudaGetErrorString(err));
+    launch_count()++;
+    return true;
+  }
   static const bool qs = []() {
     const char* e = getenv("RB200_XATTN_Q");     // default: q rows staged in shared memory (24 us vs 30 us per launch)
     return !(e && strcmp(e, "ldg") == 0);

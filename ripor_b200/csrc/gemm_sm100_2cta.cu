@@ -16,6 +16,8 @@
 // The shared-memory ring keeps streaming across tile boundaries and the TMEM accumulator is double-buffered
 // (2 x BN columns), so the epilogue of tile i overlaps the MMAs of tile i+1 and the per-tile launch / prologue /
 // drain cost of the one-tile-per-CTA version (about 5 us on a 10-25 us tile at these shapes) is paid once.
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
@@ -607,9 +609,18 @@ int launch_bn2(const GemmArgs& g, cudaStream_t s) {
     sm_pairs = sms / 2;
   }
   const int64_t m_pairs = ceil_div(g.M, 2 * BM);
-  const int64_t cost256 = (int64_t)ceil_div(m_pairs * ceil_div(g.N, 256), sm_pairs) * 256;
+  const int64_t tiles256 = m_pairs * ceil_div(g.N, 256);
+  const int64_t cost256 = (int64_t)ceil_div(tiles256, sm_pairs) * 256;
   const int64_t cost128 = (int64_t)ceil_div(m_pairs * ceil_div(g.N, 128), sm_pairs) * 128;
-  if (g.N >= 256 && cost256 <= cost128) return launch_cfg2<ELEM_BYTES, NTERMS, 256>(g, s);
+  // Many rounds per SM pair (the forced tail: M = 71680): quantisation no longer matters and the 128-wide tiles are
+  // bound by operand delivery from L2 (ncu: 9.2-9.7 TB/s L2->SM on every tail GEMM); 256-wide tiles move a third
+  // fewer operand bytes per output. RB200_BN=128|256 forces a width.
+  static const int force = []() {
+    const char* e = getenv("RB200_BN");
+    return e ? atoi(e) : 0;
+  }();
+  const bool wide = force ? force == 256 : (cost256 <= cost128 || tiles256 >= 4 * (int64_t)sm_pairs);
+  if (g.N >= 256 && wide) return launch_cfg2<ELEM_BYTES, NTERMS, 256>(g, s);
   return launch_cfg2<ELEM_BYTES, NTERMS, 128>(g, s);
 }
 

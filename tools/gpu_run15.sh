@@ -1,0 +1,7 @@
+set -x
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_gpu_parity.py -x -q --timeout 400 -k "golden or t5base_search or long_docid or wide_beam or forced_tail or t5large" 2>&1 | tail -3 | tee gpurun_out/pytest_gpu15.log
+B="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+timeout 300 $B 2>&1 | tail -1 | tee gpurun_out/bench15.json | cut -c1-250
+timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches15.csv python tools/profile_step.py --precision fp16x3 > gpurun_out/prof15.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches15.csv | tee gpurun_out/launch_summary15.txt | head -12
