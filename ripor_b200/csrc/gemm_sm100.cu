@@ -317,6 +317,7 @@ int get_tensor_map(const void* ptr, int64_t rows, int64_t k, int box_rows, int e
                 (int)r, ptr, (long long)rows, (long long)k, (long long)ld, box_rows, elem);
   {
     std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() >= 4096) cache.clear();   // callers that keep passing fresh buffers must not grow it forever
     cache[key] = m;
   }
   *out = m;
