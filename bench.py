@@ -276,6 +276,38 @@ def run_ours(a):
                         f"{prec} issues {mma_mult} tensor-core MMA(s) per algorithmic product, so frac <= 1/{mma_mult} "
                         "by construction; frac_of_split_peak = issued / peak",
                 "frac_of_split_peak": achieved * mma_mult / peak}
+    # ---- secondary: achieved HBM GB/s of the trie / top-k beam-step kernel (BASELINE north_star) on a batch whose
+    # logits (R x V fp32) do not fit L2; algorithmic bytes per launch = logits + beam/trie state in + state out ----
+    trie_topk = None
+    if rank == 0:
+        try:
+            Rq = 1 << 14                                             # queries -> 163,840 rows, 168 MB of logits at V=256
+            hb = C.c_void_p()
+            _lib.check(lib.rb200_beam_create(local, Rq, nb, L, a.codebook, C.byref(hb)))
+            big = torch.randn((Rq * nb, a.codebook), device=dev)
+            _lib.check(lib.rb200_beam_reset(hb, trie.handle, Rq, _lib.stream_ptr()))
+            _lib.check(lib.rb200_beam_step(hb, trie.handle, big.data_ptr(), 1, 0, None, None, 0, _lib.stream_ptr()))
+            b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            nlaunch = min(4, L - 1)
+            torch.cuda.synchronize()
+            b0.record()
+            for _ in range(nlaunch):
+                _lib.check(lib.rb200_beam_step(hb, trie.handle, big.data_ptr(), nb, 0, None, None, 0, _lib.stream_ptr()))
+            b1.record()
+            torch.cuda.synchronize()
+            lib.rb200_beam_free(hb)
+            us = b0.elapsed_time(b1) * 1e3 / nlaunch
+            per_row = a.codebook * 4 + (8 + 16) + (8 + 16 + 4 + 4) + 2 * L * 4 * 2   # logits, score+state in, out, hist+anc in/out
+            nbytes = Rq * nb * per_row
+            hbm = peaks.get("hbm_gbs", 6550.0)
+            trie_topk = {"kernel": "beam_step_kernel", "rows": Rq * nb, "avg_launch_us": us,
+                         "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": nbytes / us / 1e3, "peak_gbs": hbm,
+                         "frac": nbytes / us / 1e3 / hbm, "bound": "hbm",
+                         "note": "float64 candidate ranking over nb*V logits per query, trie child lookup, history / "
+                                 "ancestry reorder; one CTA per query"}
+            del big
+        except Exception as exc:                                     # the secondary figure must never break the bench line
+            trie_topk = {"error": str(exc)[:200]}
     result = {
         "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
         "ms_per_step": ms / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -287,7 +319,8 @@ def run_ours(a):
                    "global_batch": world * B, "forced_tail_from_step": tail_from,
                    "l2": "per-step working set (fp32 KV cache + weights, >6 GB) exceeds the 126 MB L2",
                    "trie_build_s": round(trie_build_s, 2), "parallelism": f"query-sharded x{world}"},
-        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps), "roofline": roofline}
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches_per_step * a.steps), "roofline": roofline,
+        "trie_topk": trie_topk}
     # ---- parity spot check + CPU baseline on rank 0 -----------------------------------------------------
     if rank == 0:
         from tests import helpers

@@ -49,7 +49,7 @@ struct StepArgs {
   int32_t* not_forced;
 };
 
-template <int THREADS>
+template <int THREADS, int KREG>   // KREG > 0: each thread keeps its (<= KREG) candidate values in registers
 __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
   constexpr int NW = THREADS / 32;
   const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -107,11 +107,35 @@ __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
   };
   uint32_t taken[kMaxPerThread / 32] = {0u, 0u, 0u, 0u};
   const int K = (total + THREADS - 1) / THREADS;
+  // The thread that owns a winner looks for its next best candidate while everybody else waits at the barrier of the
+  // next round: with the values cached in registers that is K compares instead of K x (division, logit load, bitmap
+  // lookup, float64 add).
+  constexpr int KR = KREG > 0 ? KREG : 1;
+  const bool cached = KREG > 0 && K <= KREG;
+  double cv[KR];
+  if (cached) {
+#pragma unroll
+    for (int k = 0; k < KR; ++k) {
+      const int c = tid + k * THREADS;
+      cv[k] = (k < K && c < total) ? cand_val(c) : 0.0;
+    }
+  }
   double best_v;
   int best_c;
   auto rescan = [&]() {
     best_v = -INFINITY;
     best_c = INT_MAX;
+    if (cached) {
+#pragma unroll
+      for (int k = 0; k < KR; ++k) {
+        const int c = tid + k * THREADS;
+        if (k < K && c < total && !((taken[0] >> k) & 1u) && cand_better(cv[k], c, best_v, best_c)) {
+          best_v = cv[k];
+          best_c = c;
+        }
+      }
+      return;
+    }
     for (int k = 0; k < K; ++k) {
       const int c = tid + k * THREADS;
       if (c < total && !((taken[k >> 5] >> (k & 31)) & 1u)) {
@@ -152,16 +176,53 @@ __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
 
   rb::pdl_trigger();   // selection done; only the state write-back remains
   // ---- C. new beam state: scores, trie child, token history, KV ancestry, next decoder input --------
-  for (int j = tid; j < nb; j += THREADS) {
+  // one warp per new beam: the child lookup (rb::trie_child, restated warp-wide) reads up to RB_TRIE_SMALL code rows
+  // or the node's bitmap words, which a single thread would fetch one dependent load after the other
+  for (int j = warp; j < nb; j += NW) {
     const int c = win_idx[j];
     const int i = c / V, v = c - i * V;
     const int r_new = b * nb + j;
-    a.sc_new[r_new] = win_val[j];
-    a.parent_out[r_new] = i;
-    a.token_out[r_new] = v;
-    const TrieState ns = rb::trie_child(a.tv, a.st_old[b * nb + i], t, v);
-    a.st_new[r_new] = ns;
-    if (ns.hi - ns.lo != 1) atomicAdd(a.not_forced, 1);   // not (yet) a single leaf: the tail cannot be forced
+    const TrieState s = a.st_old[b * nb + i];
+    const int n = s.hi - s.lo;
+    TrieState ns = rb::trie_dead();
+    if (n > 0 && t < a.tv.L && v >= 0 && v < V) {
+      if (s.node >= 0) {
+        const uint32_t* bm = a.tv.node_bitmap + (int64_t)s.node * words;
+        const int w = v >> 5;
+        const uint32_t bit = 1u << (v & 31);
+        int k = 0;
+        uint32_t wv = 0;
+        for (int w0 = 0; w0 <= w; w0 += 32) {                       // popcount rank of v among the node's children
+          const int wi = w0 + lane;
+          const uint32_t x = wi <= w ? bm[wi] : 0u;
+          if (wi == w) wv = x;
+          int part = wi < w ? __popc(x) : (wi == w ? __popc(x & (bit - 1u)) : 0);
+          for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+          k += part;
+        }
+        wv = __shfl_sync(0xffffffffu, wv, w & 31);
+        if (wv & bit) {
+          const int cidx = a.tv.node_child_ptr[s.node] + k;
+          ns = TrieState{a.tv.child_lo[cidx], a.tv.child_lo[cidx + 1], a.tv.child_node[cidx], 0};
+        }
+      } else {
+        int less = 0, leq = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {                        // n <= RB_TRIE_SMALL: one round
+          const bool in = j0 + lane < n;
+          const int cc = in ? rb::trie_code(a.tv, (int64_t)s.lo + j0 + lane, t) : INT_MAX;
+          less += __popc(__ballot_sync(0xffffffffu, in && cc < v));
+          leq += __popc(__ballot_sync(0xffffffffu, in && cc <= v));
+        }
+        if (leq != less) ns = TrieState{s.lo + less, s.lo + leq, -1, 0};
+      }
+    }
+    if (lane == 0) {
+      a.sc_new[r_new] = win_val[j];
+      a.parent_out[r_new] = i;
+      a.token_out[r_new] = v;
+      a.st_new[r_new] = ns;
+      if (ns.hi - ns.lo != 1) atomicAdd(a.not_forced, 1);   // not (yet) a single leaf: the tail cannot be forced
+    }
   }
   const int L = a.L;
   for (int e = tid; e < nb * L; e += THREADS) {
@@ -368,9 +429,12 @@ int rb200_beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits,
                       (size_t)nb * a.tv.words * sizeof(uint32_t);
   const int64_t total = (int64_t)nb * bm->V;
   if (total <= 256 * 32) {
-    RB_CUDA(rb::launch_pdl(beam_step_kernel<256>, dim3(bm->batch), dim3(256), smem, (cudaStream_t)stream, a));
+    if (total <= 256 * 16)
+      RB_CUDA(rb::launch_pdl(beam_step_kernel<256, 16>, dim3(bm->batch), dim3(256), smem, (cudaStream_t)stream, a));
+    else
+      RB_CUDA(rb::launch_pdl(beam_step_kernel<256, 32>, dim3(bm->batch), dim3(256), smem, (cudaStream_t)stream, a));
   } else {
-    RB_CUDA(rb::launch_pdl(beam_step_kernel<1024>, dim3(bm->batch), dim3(1024), smem, (cudaStream_t)stream, a));
+    RB_CUDA(rb::launch_pdl(beam_step_kernel<1024, 0>, dim3(bm->batch), dim3(1024), smem, (cudaStream_t)stream, a));
   }
   rb::launch_count()++;
   bm->cur = n;

@@ -1,3 +1,4 @@
+# Round-end validation on one B200: GPU parity suite, smoke, the default bench line, the launch list of one search.
 set -x
 mkdir -p gpurun_out
 timeout 1200 python -m pytest tests -m gpu -x -q --timeout 400 2>&1 | tail -6 | tee gpurun_out/pytest_gpu_final.log
@@ -6,5 +7,3 @@ timeout 400 python bench.py --steps 5 --warmup 3 2>&1 | tail -1 | tee gpurun_out
 P="python tools/profile_step.py --precision fp16x3"
 timeout 400 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_final.csv $P > gpurun_out/prof_final.log 2>&1
 python tools/summarize_launches.py gpurun_out/launches_final.csv | tee gpurun_out/launch_summary_final.txt | head -12
-timeout 400 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:"tail_mma16|cross_attn_mma16" -c 2 -o gpurun_out/r01_attn_mma $P > gpurun_out/proff5.log 2>&1
-ls -la gpurun_out/r01_attn_mma.ncu-rep
