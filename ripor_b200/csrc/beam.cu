@@ -16,6 +16,8 @@
 #include <cfloat>
 #include <climits>
 #include <cmath>
+#include <cstdlib>
+#include <cstring>
 
 #include "beam.h"
 
@@ -248,6 +250,175 @@ __global__ void __launch_bounds__(THREADS) beam_step_kernel(const StepArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-per-query formulation of the same step (nb <= kWarpNb): no block barriers. Every lane keeps the best nb of its
+// own candidates (flat index = lane + 32 k) in a small sorted list; the nb winners are then popped with warp-wide
+// arg-max rounds over the list heads. The global top-nb under (value desc, flat index asc) is contained in the union
+// of the per-lane top-nb lists, so the result is identical to the block kernel's (and to the reference's top-k).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kWarpNb = 16;          // beams per query this kernel handles
+constexpr int kWarpQ = 4;            // queries (warps) per CTA
+constexpr int kListLd = kWarpNb + 1; // padded per-lane list stride
+
+__global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepArgs a, int batch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kWarpQ + warp;
+  const int nb = a.nb, V = a.tv.V, words = a.tv.words, t = a.t, L = a.L;
+  const int total = nb * V;
+  rb::pdl_wait();
+  if (b >= batch) return;
+
+  extern __shared__ __align__(16) unsigned char wsmem_raw[];
+  // per warp: list values [32][kListLd] f64 | list indices [32][kListLd] i32 | bs[kWarpNb] f64 | win_val[kWarpNb] f64 |
+  //           win_idx[kWarpNb] | row_max, row_log [kWarpNb] f32 | allow[kWarpNb * words]
+  const size_t per_warp = 32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4) + (size_t)kWarpNb * words * 4;
+  unsigned char* base = wsmem_raw + warp * ((per_warp + 15) & ~(size_t)15);
+  double* list_v = reinterpret_cast<double*>(base);
+  double* bs = list_v + 32 * kListLd;
+  double* win_val = bs + kWarpNb;
+  int* list_c = reinterpret_cast<int*>(win_val + kWarpNb);
+  int* win_idx = list_c + 32 * kListLd;
+  float* row_max = reinterpret_cast<float*>(win_idx + kWarpNb);
+  float* row_log = row_max + kWarpNb;
+  uint32_t* allow = reinterpret_cast<uint32_t*>(row_log + kWarpNb);
+
+  // ---- A. allowed-children bitmaps, beam scores, optional log-softmax statistics ---------------------------------
+  for (int i = 0; i < nb; ++i) {
+    const TrieState s = a.st_old[b * nb + i];
+    uint32_t* bm = allow + i * words;
+    const int n = s.hi - s.lo;
+    for (int w = lane; w < words; w += 32)
+      bm[w] = (n > 0 && s.node >= 0 && t < a.tv.L) ? a.tv.node_bitmap[(int64_t)s.node * words + w] : 0u;
+    __syncwarp();
+    if (n > 0 && s.node < 0 && t < a.tv.L && lane < n) {
+      const int v = rb::trie_code(a.tv, (int64_t)s.lo + lane, t);
+      atomicOr(&bm[v >> 5], 1u << (v & 31));
+    }
+    if (lane == 0) bs[i] = a.sc_old[b * nb + i];
+    if (a.apply_ls) {
+      const float* row = a.logits + (int64_t)(b * a.rpq + (a.rpq == 1 ? 0 : i)) * V;
+      float m = -INFINITY;
+      for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
+      for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+      float sum = 0.f;
+      for (int v = lane; v < V; v += 32) sum += expf(row[v] - m);
+      for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+      if (lane == 0) { row_max[i] = m; row_log[i] = logf(sum); }
+    }
+  }
+  __syncwarp();
+
+  // ---- B1. every lane: sorted list of its best nb candidates -------------------------------------------------------
+  double* lv = list_v + lane * kListLd;
+  int* lc = list_c + lane * kListLd;
+  int cnt = 0;
+  {
+    // walk (beam i, token v) with flat index c = i * V + v = lane + 32 k without divisions
+    int i = 0, v = lane;
+    while (v >= V) { v -= V; ++i; }
+    for (int c = lane; c < total; c += 32) {
+      float x = a.logits[(int64_t)(b * a.rpq + (a.rpq == 1 ? 0 : i)) * V + v];
+      if (a.apply_ls) x = (x - row_max[i]) - row_log[i];
+      const bool ok = (allow[i * words + (v >> 5)] >> (v & 31)) & 1u;
+      const double processed = ok ? (double)x : (double)x + (-1e9);   // s + (1 - mask) * (-1e9)
+      double val = processed + bs[i];
+      val = val == val ? val : -1.7976931348623157e308;                // NaN logits rank last, by index
+      if (cnt < nb || cand_better(val, c, lv[cnt - 1], lc[cnt - 1])) {
+        int pos = cnt < nb ? cnt : nb - 1;                              // a full list drops its last entry
+        while (pos > 0 && cand_better(val, c, lv[pos - 1], lc[pos - 1])) {
+          lv[pos] = lv[pos - 1];
+          lc[pos] = lc[pos - 1];
+          --pos;
+        }
+        lv[pos] = val;
+        lc[pos] = c;
+        if (cnt < nb) ++cnt;
+      }
+      v += 32;
+      while (v >= V) { v -= V; ++i; }
+    }
+  }
+  // ---- B2. nb rounds of warp arg-max over the list heads ---------------------------------------------------------
+  int hd = 0;
+  for (int j = 0; j < nb; ++j) {
+    double v = hd < cnt ? lv[hd] : -INFINITY;
+    int c = hd < cnt ? lc[hd] : INT_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, c, o);
+      if (cand_better(ov, oc, v, c)) { v = ov; c = oc; }
+    }
+    if (hd < cnt && lc[hd] == c) ++hd;                                  // the owner pops its head
+    if (lane == 0) { win_val[j] = v; win_idx[j] = c; }
+  }
+  __syncwarp();
+  rb::pdl_trigger();
+
+  // ---- C. new beam state ----------------------------------------------------------------------------------------------
+  for (int j = 0; j < nb; ++j) {
+    const int c = win_idx[j];
+    const int i = c / V, v = c - i * V;
+    const int r_new = b * nb + j;
+    const TrieState s = a.st_old[b * nb + i];
+    const int n = s.hi - s.lo;
+    TrieState ns = rb::trie_dead();
+    if (n > 0 && t < a.tv.L && v >= 0 && v < V) {
+      if (s.node >= 0) {
+        const uint32_t* bm = a.tv.node_bitmap + (int64_t)s.node * words;
+        const int w = v >> 5;
+        const uint32_t bit = 1u << (v & 31);
+        int k = 0;
+        uint32_t wv = 0;
+        for (int w0 = 0; w0 <= w; w0 += 32) {
+          const int wi = w0 + lane;
+          const uint32_t x = wi <= w ? bm[wi] : 0u;
+          if (wi == w) wv = x;
+          const int part = wi < w ? __popc(x) : (wi == w ? __popc(x & (bit - 1u)) : 0);
+          k += __reduce_add_sync(0xffffffffu, part);
+        }
+        wv = __shfl_sync(0xffffffffu, wv, w & 31);
+        if (wv & bit) {
+          const int cidx = a.tv.node_child_ptr[s.node] + k;
+          ns = TrieState{a.tv.child_lo[cidx], a.tv.child_lo[cidx + 1], a.tv.child_node[cidx], 0};
+        }
+      } else {
+        int less = 0, leq = 0;
+        for (int j0 = 0; j0 < n; j0 += 32) {
+          const bool in = j0 + lane < n;
+          const int cc = in ? rb::trie_code(a.tv, (int64_t)s.lo + j0 + lane, t) : INT_MAX;
+          less += __popc(__ballot_sync(0xffffffffu, in && cc < v));
+          leq += __popc(__ballot_sync(0xffffffffu, in && cc <= v));
+        }
+        if (leq != less) ns = TrieState{s.lo + less, s.lo + leq, -1, 0};
+      }
+    }
+    if (lane == 0) {
+      a.sc_new[r_new] = win_val[j];
+      a.parent_out[r_new] = i;
+      a.token_out[r_new] = v;
+      a.st_new[r_new] = ns;
+      if (ns.hi - ns.lo != 1) atomicAdd(a.not_forced, 1);
+    }
+    // token history and KV ancestry of the new beam (lane = position)
+    const int src = b * nb + i, dst = r_new;
+    for (int p = lane; p < L; p += 32) {
+      a.hist_new[dst * L + p] = p < t ? a.hist_old[src * L + p] : (p == t ? v : 0);
+      int anc;
+      if (p < t) anc = a.anc_old[src * L + p];
+      else if (p == t) anc = (a.rpq == 1) ? b : src;
+      else if (p == t + 1) anc = dst;
+      else anc = 0;
+      a.anc_new[dst * L + p] = anc;
+    }
+    if (a.embed_table != nullptr) {                                      // next decoder input row (d_model % 4 == 0)
+      const float4* srcv = reinterpret_cast<const float4*>(a.embed_table + (int64_t)v * a.d_model);
+      float4* dstv = reinterpret_cast<float4*>(a.next_x + (int64_t)r_new * a.d_model);
+      for (int e = lane; e < (a.d_model >> 2); e += 32) dstv[e] = srcv[e];
+    }
+  }
+}
+
 __global__ void beam_reset_kernel(TrieView tv, int nb, int L, int batch, double* sc, TrieState* st, int32_t* hist,
                                   int32_t* anc) {
   const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -428,7 +599,16 @@ int rb200_beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits,
   const size_t smem = (2 * nb + 32) * sizeof(double) + (32 + nb) * sizeof(int) + 2 * nb * sizeof(float) +
                       (size_t)nb * a.tv.words * sizeof(uint32_t);
   const int64_t total = (int64_t)nb * bm->V;
-  if (total <= 256 * 32) {
+  static const bool force_cta = []() {
+    const char* e = getenv("RB200_BEAM");
+    return e && strcmp(e, "cta") == 0;
+  }();
+  if (!force_cta && nb <= kWarpNb && d_model % 4 == 0) {
+    const size_t per_warp = (32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4) + (size_t)kWarpNb * a.tv.words * 4 + 15) &
+                            ~(size_t)15;
+    RB_CUDA(rb::launch_pdl(beam_step_warp_kernel, dim3(rb::ceil_div(bm->batch, kWarpQ)), dim3(kWarpQ * 32),
+                           kWarpQ * per_warp, (cudaStream_t)stream, a, bm->batch));
+  } else if (total <= 256 * 32) {
     if (total <= 256 * 16)
       RB_CUDA(rb::launch_pdl(beam_step_kernel<256, 16>, dim3(bm->batch), dim3(256), smem, (cudaStream_t)stream, a));
     else
