@@ -283,19 +283,36 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   uint32_t* allow = reinterpret_cast<uint32_t*>(row_log + kWarpNb);
 
   // ---- A. allowed-children bitmaps, beam scores, optional log-softmax statistics ---------------------------------
-  for (int i = 0; i < nb; ++i) {
-    const TrieState s = a.st_old[b * nb + i];
-    uint32_t* bm = allow + i * words;
-    const int n = s.hi - s.lo;
-    for (int w = lane; w < words; w += 32)
-      bm[w] = (n > 0 && s.node >= 0 && t < a.tv.L) ? a.tv.node_bitmap[(int64_t)s.node * words + w] : 0u;
-    __syncwarp();
-    if (n > 0 && s.node < 0 && t < a.tv.L && lane < n) {
-      const int v = rb::trie_code(a.tv, (int64_t)s.lo + lane, t);
-      atomicOr(&bm[v >> 5], 1u << (v & 31));
+  // The trie tables are far larger than L2 (codes: 280 MB at 8.8 M documents), so every lookup is a DRAM round trip:
+  // the loads of all nb beams are issued together instead of one beam after the other.
+  const TrieState my = lane < nb ? a.st_old[b * nb + lane] : rb::trie_dead();   // lane i = beam i
+  if (lane < nb) bs[lane] = a.sc_old[b * nb + lane];
+  {
+    const int nbw = nb * words;
+    for (int idx0 = 0; idx0 < nbw; idx0 += 32) {                    // explicit nodes: (beam, word) pairs over the lanes
+      const int idx = min(idx0 + lane, nbw - 1);
+      const int i = idx / words, w = idx - i * words;
+      const int node_i = __shfl_sync(0xffffffffu, my.node, i);
+      const int n_i = __shfl_sync(0xffffffffu, my.hi - my.lo, i);
+      if (idx0 + lane < nbw)
+        allow[idx] = (n_i > 0 && node_i >= 0 && t < a.tv.L) ? a.tv.node_bitmap[(int64_t)node_i * words + w] : 0u;
     }
-    if (lane == 0) bs[i] = a.sc_old[b * nb + i];
-    if (a.apply_ls) {
+    __syncwarp();
+    int code[kWarpNb];                                              // implicit ranges: column t of their <= 32 rows
+#pragma unroll
+    for (int i = 0; i < kWarpNb; ++i) {
+      const int node_i = __shfl_sync(0xffffffffu, my.node, i & 31);
+      const int lo_i = __shfl_sync(0xffffffffu, my.lo, i & 31);
+      const int n_i = __shfl_sync(0xffffffffu, my.hi - my.lo, i & 31);
+      code[i] = (i < nb && n_i > 0 && node_i < 0 && t < a.tv.L && lane < n_i)
+                    ? rb::trie_code(a.tv, (int64_t)lo_i + lane, t) : -1;
+    }
+#pragma unroll
+    for (int i = 0; i < kWarpNb; ++i)
+      if (code[i] >= 0) atomicOr(&allow[i * words + (code[i] >> 5)], 1u << (code[i] & 31));
+  }
+  if (a.apply_ls) {
+    for (int i = 0; i < nb; ++i) {
       const float* row = a.logits + (int64_t)(b * a.rpq + (a.rpq == 1 ? 0 : i)) * V;
       float m = -INFINITY;
       for (int v = lane; v < V; v += 32) m = fmaxf(m, row[v]);
@@ -355,54 +372,59 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   __syncwarp();
   rb::pdl_trigger();
 
-  // ---- C. new beam state ----------------------------------------------------------------------------------------------
-  for (int j = 0; j < nb; ++j) {
-    const int c = win_idx[j];
-    const int i = c / V, v = c - i * V;
-    const int r_new = b * nb + j;
-    const TrieState s = a.st_old[b * nb + i];
-    const int n = s.hi - s.lo;
-    TrieState ns = rb::trie_dead();
-    if (n > 0 && t < a.tv.L && v >= 0 && v < V) {
-      if (s.node >= 0) {
-        const uint32_t* bm = a.tv.node_bitmap + (int64_t)s.node * words;
-        const int w = v >> 5;
-        const uint32_t bit = 1u << (v & 31);
-        int k = 0;
-        uint32_t wv = 0;
-        for (int w0 = 0; w0 <= w; w0 += 32) {
-          const int wi = w0 + lane;
-          const uint32_t x = wi <= w ? bm[wi] : 0u;
-          if (wi == w) wv = x;
-          const int part = wi < w ? __popc(x) : (wi == w ? __popc(x & (bit - 1u)) : 0);
-          k += __reduce_add_sync(0xffffffffu, part);
-        }
-        wv = __shfl_sync(0xffffffffu, wv, w & 31);
-        if (wv & bit) {
-          const int cidx = a.tv.node_child_ptr[s.node] + k;
-          ns = TrieState{a.tv.child_lo[cidx], a.tv.child_lo[cidx + 1], a.tv.child_node[cidx], 0};
-        }
-      } else {
-        int less = 0, leq = 0;
-        for (int j0 = 0; j0 < n; j0 += 32) {
-          const bool in = j0 + lane < n;
-          const int cc = in ? rb::trie_code(a.tv, (int64_t)s.lo + j0 + lane, t) : INT_MAX;
-          less += __popc(__ballot_sync(0xffffffffu, in && cc < v));
-          leq += __popc(__ballot_sync(0xffffffffu, in && cc <= v));
-        }
-        if (leq != less) ns = TrieState{s.lo + less, s.lo + leq, -1, 0};
-      }
+  // ---- C. new beam state: lane j = new beam j; again all dependent trie loads of the nb beams overlap ------------
+  const int cj = lane < nb ? win_idx[lane] : 0;
+  const int pj = cj / V, vj = cj - pj * V;                          // parent beam, token
+  const TrieState sj = lane < nb ? a.st_old[b * nb + pj] : rb::trie_dead();
+  const int nj = sj.hi - sj.lo;
+  const bool live = lane < nb && nj > 0 && t < a.tv.L;
+  TrieState ns = rb::trie_dead();
+  if (live && sj.node >= 0) {                                       // explicit node: popcount rank, then the child slot
+    const uint32_t* bm = a.tv.node_bitmap + (int64_t)sj.node * words;
+    const int w = vj >> 5;
+    const uint32_t bit = 1u << (vj & 31);
+    int k = 0;
+    for (int wi = 0; wi < w; ++wi) k += __popc(bm[wi]);
+    const uint32_t wv = bm[w];
+    if (wv & bit) {
+      const int cidx = a.tv.node_child_ptr[sj.node] + k + __popc(wv & (bit - 1u));
+      ns = TrieState{a.tv.child_lo[cidx], a.tv.child_lo[cidx + 1], a.tv.child_node[cidx], 0};
     }
-    if (lane == 0) {
-      a.sc_new[r_new] = win_val[j];
-      a.parent_out[r_new] = i;
-      a.token_out[r_new] = v;
-      a.st_new[r_new] = ns;
-      if (ns.hi - ns.lo != 1) atomicAdd(a.not_forced, 1);
+  }
+  {                                                                 // implicit ranges: warp-wide count per beam
+    int code[kWarpNb];
+#pragma unroll
+    for (int j = 0; j < kWarpNb; ++j) {
+      const int node_j = __shfl_sync(0xffffffffu, sj.node, j & 31);
+      const int lo_j = __shfl_sync(0xffffffffu, sj.lo, j & 31);
+      const int n_j = __shfl_sync(0xffffffffu, live ? nj : 0, j & 31);
+      code[j] = (j < nb && n_j > 0 && node_j < 0 && lane < n_j) ? rb::trie_code(a.tv, (int64_t)lo_j + lane, t) : INT_MAX;
     }
-    // token history and KV ancestry of the new beam (lane = position)
-    const int src = b * nb + i, dst = r_new;
-    for (int p = lane; p < L; p += 32) {
+#pragma unroll
+    for (int j = 0; j < kWarpNb; ++j) {
+      const int v_j = __shfl_sync(0xffffffffu, vj, j & 31);
+      const int less = __popc(__ballot_sync(0xffffffffu, code[j] < v_j));
+      const int leq = __popc(__ballot_sync(0xffffffffu, code[j] <= v_j));   // INT_MAX never counts (v_j < V)
+      if (lane == j && live && sj.node < 0 && leq != less) ns = TrieState{sj.lo + less, sj.lo + leq, -1, 0};
+    }
+  }
+  if (lane < nb) {
+    const int r_new = b * nb + lane;
+    a.sc_new[r_new] = win_val[lane];
+    a.parent_out[r_new] = pj;
+    a.token_out[r_new] = vj;
+    a.st_new[r_new] = ns;
+    if (ns.hi - ns.lo != 1) atomicAdd(a.not_forced, 1);
+  }
+  // token history and KV ancestry of the new beams: (beam j, position p) pairs over the lanes
+  {
+    const int tot = nb * L;
+#pragma unroll 4
+    for (int e = lane; e < tot; e += 32) {
+      const int j = e / L, p = e - j * L;
+      const int c = win_idx[j];
+      const int i = c / V, v = c - i * V;
+      const int src = b * nb + i, dst = b * nb + j;
       a.hist_new[dst * L + p] = p < t ? a.hist_old[src * L + p] : (p == t ? v : 0);
       int anc;
       if (p < t) anc = a.anc_old[src * L + p];
@@ -411,10 +433,15 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
       else anc = 0;
       a.anc_new[dst * L + p] = anc;
     }
-    if (a.embed_table != nullptr) {                                      // next decoder input row (d_model % 4 == 0)
-      const float4* srcv = reinterpret_cast<const float4*>(a.embed_table + (int64_t)v * a.d_model);
-      float4* dstv = reinterpret_cast<float4*>(a.next_x + (int64_t)r_new * a.d_model);
-      for (int e = lane; e < (a.d_model >> 2); e += 32) dstv[e] = srcv[e];
+  }
+  if (a.embed_table != nullptr) {                                    // next decoder input rows (d_model % 4 == 0)
+    const int d4 = a.d_model >> 2, tot = nb * d4;
+#pragma unroll 4
+    for (int e = lane; e < tot; e += 32) {
+      const int j = e / d4, col = e - j * d4;
+      const int v = win_idx[j] % V;
+      reinterpret_cast<float4*>(a.next_x + (int64_t)(b * nb + j) * a.d_model)[col] =
+          reinterpret_cast<const float4*>(a.embed_table + (int64_t)v * a.d_model)[col];
     }
   }
 }
