@@ -110,3 +110,15 @@ def test_no_cpu_fallback_exists():
     if not torch.cuda.is_available():
         with pytest.raises(_lib.RB200Error):
             model.base_model.get_engine(1, 2, 8)
+
+
+def test_new_entry_points_validate_arguments_without_a_gpu():
+    """Argument checks come before any CUDA call: they must answer (not crash) on a box without a GPU."""
+    import ctypes as C
+    L = _lib.lib()
+    us = C.c_double()
+    assert L.rb200_gemm_bench(9, 128, 128, 64, 0, 1, 0, C.byref(us), None) != 0      # unknown precision
+    assert L.rb200_gemm_bench(5, 128, 128, 64, 7, 1, 0, C.byref(us), None) != 0      # unknown epilogue
+    assert L.rb200_gemm_bench(5, 0, 128, 64, 0, 1, 0, C.byref(us), None) != 0        # empty problem
+    assert b"precision" in L.rb200_last_error() or b"bad argument" in L.rb200_last_error()
+    assert L.rb200_engine_last_tail_step(None) == -1
