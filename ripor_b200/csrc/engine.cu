@@ -228,6 +228,8 @@ static float half_bits_to_float(uint16_t h) {
   return f;
 }
 
+static int engine_build(rb200_engine* e, const rb200_engine_config* cfg);
+
 extern "C" {
 
 int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
@@ -244,6 +246,19 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
   RB_CUDA(cudaSetDevice(cfg->device));
   rb200_engine* e = new (std::nothrow) rb200_engine();
   if (!e) return rb::fail(RB200_ERR_NOMEM, "out of memory");
+  const int st = engine_build(e, cfg);
+  if (st != 0) {                      // e.g. out of device memory half way: give everything back (keeps last_error)
+    rb200_engine_free(e);
+    return st;
+  }
+  *out = e;
+  return 0;
+}
+
+}  // extern "C"
+
+// allocations of rb200_engine_create; on failure the caller frees whatever was allocated so far
+static int engine_build(rb200_engine* e, const rb200_engine_config* cfg) {
   e->cfg = *cfg;
   e->mode = cfg->precision;
   e->planes = rb::prec_planes(e->mode);
@@ -342,9 +357,10 @@ int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out) {
   RB_TRY(dev_alloc(e, (void**)&e->leaf_dev, Rall * 2 * 4));
   RB_TRY(dev_alloc(e, (void**)&e->overflow, 2 * 4));
   RB_CUDA(cudaMemset(e->overflow, 0, 8));
-  *out = e;
   return 0;
 }
+
+extern "C" {
 
 int rb200_engine_free(rb200_engine* e) {
   if (!e) return 0;
