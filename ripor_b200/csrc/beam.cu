@@ -630,9 +630,10 @@ int rb200_beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits,
     const char* e = getenv("RB200_BEAM");
     return e && strcmp(e, "cta") == 0;
   }();
-  if (!force_cta && nb <= kWarpNb && d_model % 4 == 0) {
-    const size_t per_warp = (32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4) + (size_t)kWarpNb * a.tv.words * 4 + 15) &
-                            ~(size_t)15;
+  const size_t per_warp = (32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4) + (size_t)kWarpNb * a.tv.words * 4 + 15) &
+                          ~(size_t)15;
+  // (very wide codebooks would push the per-warp bitmaps past the default 48 KB of dynamic shared memory)
+  if (!force_cta && nb <= kWarpNb && d_model % 4 == 0 && kWarpQ * per_warp <= 48 * 1024) {
     RB_CUDA(rb::launch_pdl(beam_step_warp_kernel, dim3(rb::ceil_div(bm->batch, kWarpQ)), dim3(kWarpQ * 32),
                            kWarpQ * per_warp, (cudaStream_t)stream, a, bm->batch));
   } else if (total <= 256 * 32) {
