@@ -68,6 +68,11 @@ int rb200_trie_level_counts(const rb200_trie* trie, int64_t* counts_host);
 /* versioned binary cache replacing list_smtid_to_nextids.pkl (evaluate.py:404-432). */
 int rb200_trie_save(const rb200_trie* trie, const char* path);
 int rb200_trie_load(const char* path, rb200_trie** out);
+/* same, with a caller-chosen 64-bit tag of the SOURCE the trie was built from (e.g. size/mtime/hash of
+ * docid_to_smtid.json) stored in the header, so that a stale cache is detected instead of silently mapping beams to
+ * the wrong documents. The file is written under a temporary name and renamed into place. */
+int rb200_trie_save_tagged(const rb200_trie* trie, const char* path, uint64_t source_tag);
+int rb200_trie_load_tagged(const char* path, uint64_t* source_tag, rb200_trie** out);
 /* Host walk with the semantics of PrefixConstrainLogitProcessorFastSparse.__call__ (generation.py:666-677):
  * input_ids_host [R, T] int64 (column 0 is the decoder start token and is ignored), mask_host [R, V]
  * float64: 1.0 on allowed next tokens, all-zero row for a prefix that is not in the trie. */
@@ -79,11 +84,41 @@ int rb200_trie_mask_host(const rb200_trie* trie, const int64_t* input_ids_host, 
 int rb200_trie_leaf_docs(const rb200_trie* trie, int64_t leaf, const int64_t** docs_host, int64_t* n);
 /* exact-match lookup of a full code row; *leaf = -1 if absent. code_host has L entries (int32). */
 int rb200_trie_find_leaf(const rb200_trie* trie, const int32_t* code_host, int64_t* leaf);
-/* copy the tables to HBM of `device` (idempotent). */
+/* copy the tables to HBM of `device` (idempotent; one device per handle: one process per GPU, as the reference
+ * runs, evaluate.py:463-470). */
 int rb200_trie_upload(rb200_trie* trie, int device);
+/* Device form of the smtid -> docids mapping (evaluate.py:118-128, 439-446): leaf_ranges_dev int32 [n, 2] as
+ * returned by rb200_beam_finalize / rb200_engine_search; docs_dev int64 [n, max_docs_per_row] receives the input rows
+ * (= positions in docid_to_smtid.json) of the documents under each range in json order, padded with -1;
+ * counts_dev int32 [n] the true number of documents (0: the row is not in the trie, the reference prints and skips
+ * it; > max_docs_per_row: the row was not expanded, use rb200_trie_leaf_docs on the host). The leaf table
+ * (8 bytes per document) is uploaded on first use. */
+int rb200_trie_leaf_expand(rb200_trie* trie, const int32_t* leaf_ranges_dev, int64_t n, int max_docs_per_row,
+                           int64_t* docs_dev, int32_t* counts_dev, void* stream);
 /* Device form of the mask processor call: same semantics as rb200_trie_mask_host, all pointers on device. */
 int rb200_trie_mask_device(const rb200_trie* trie, const int64_t* input_ids_dev, int64_t R, int T,
                            double* mask_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * On-disk inputs. docid_to_smtid.json = {"<docid>": [-1, c1, .., cL], ...} (written by the reference's
+ * aq_preprocess/create_customized_smtid_file.py:47-58, read with ujson.load at evaluate.py:400-401): a streaming
+ * parser into a codes matrix and a docid string table in file order. max_len > 0 keeps only the first max_len codes
+ * of every document (evaluate.py:443: smtids[1:1+max_new_token_for_docid]).
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct rb200_docid_table rb200_docid_table;
+int rb200_docid_json_open(const char* path, int max_len, rb200_docid_table** out);
+int rb200_docid_json_free(rb200_docid_table* table);
+int rb200_docid_json_info(const rb200_docid_table* table, int64_t* n_docs, int32_t* L, int32_t* max_code,
+                          int64_t* key_bytes);
+/* int32 [n_docs, L] codes (valid until rb200_docid_json_free). */
+int rb200_docid_json_codes(const rb200_docid_table* table, const int32_t** codes_host);
+/* docid i = key_bytes[key_offsets[i] .. key_offsets[i+1]) (UTF-8, not terminated). */
+int rb200_docid_json_keys(const rb200_docid_table* table, const char** key_bytes_host, const int64_t** key_offsets_host);
+int rb200_trie_build_from_table(const rb200_docid_table* table, int V, int n_threads, rb200_trie** out);
+/* Residual-quantiser codes as faiss packs them: M codes of `bits` bits each, LSB first, in code_size bytes per
+ * vector; the reference unpacks them with faiss.BitstringReader when bits != 8
+ * (aq_preprocess/create_customized_smtid_file.py:38-45). out_host int32 [n, M]. */
+int rb200_unpack_codes(const uint8_t* packed_host, int64_t n, int64_t code_size, int M, int bits, int32_t* out_host);
 
 /* ------------------------------------------------------------------------------------------------
  * Beam state + beam step. Replaces, per decoding step, generation.py:453-463 (optional log-softmax,
@@ -98,6 +133,10 @@ int rb200_beam_free(rb200_beam* beam);
 /* start a batch of `batch` queries: beam 0 score 0, beams 1.. score -1e9 (generation.py:418-420),
  * every beam at the trie root, step counter 0. */
 int rb200_beam_reset(rb200_beam* beam, const rb200_trie* trie, int batch, void* stream);
+/* same with fewer beams than the state was created for (1 <= num_beams <= the num_beams of rb200_beam_create): the
+ * reference builds a new BeamSearchScorer per generate call (generation.py:222-229), so the beam width is a per-call
+ * argument there too. */
+int rb200_beam_reset_beams(rb200_beam* beam, const rb200_trie* trie, int batch, int num_beams, void* stream);
 /* One step. logits_dev: fp32 [batch*rows_per_query, V]; rows_per_query is 1 when all beams of a query
  * share one logits row (step 0: identical prefixes) or num_beams. apply_log_softmax mirrors
  * apply_log_softmax_for_scores. If next_embed_table_dev != NULL (fp32 [V, d_model], the reference's
@@ -118,6 +157,14 @@ int rb200_beam_finalize(rb200_beam* beam, const rb200_trie* trie, int num_return
  * what = 0: beam_scores f64 [batch*nb]; 1: parent (in-query beam index) i32 [batch*nb];
  * 2: last tokens i32 [batch*nb]; 3: token history i32 [batch*nb, L]; 4: KV ancestry i32 [batch*nb, L];
  * 5: trie state i32 [batch*nb, 4] (lo, hi, node, 0). */
+/* Forced-tail score replay (the part of the engine's forced tail that is beam arithmetic), exposed for parity tests:
+ * the state must sit at step t with every beam of every query on a single trie leaf. tail_logits_dev: fp32
+ * [T, batch*num_beams, V], block j = the logits of step t+j for the beams IN THEIR ORDER AT STEP t (a lineage's
+ * logits do not depend on the slot it occupies). Leaves scores, token history, trie state and beam order exactly
+ * where T more rb200_beam_step calls on the same logits would (float64 adds in step order and the per-step
+ * re-ranking of generation.py:463-507). t + T <= 32. */
+int rb200_beam_forced_tail(rb200_beam* beam, const rb200_trie* trie, int T, const float* tail_logits_dev,
+                           int apply_log_softmax, void* stream);
 int rb200_beam_view(const rb200_beam* beam, int what, const void** ptr_dev);
 int rb200_beam_current_step(const rb200_beam* beam);
 
@@ -149,8 +196,8 @@ typedef struct {
   int32_t docid_len;                  /* number of codebook positions the model has tables for */
   int32_t shared_output_input_embeds; /* t5_generative_retriever.py:254-258 */
   int32_t scaleup_output_hidden;      /* t5_generative_retriever.py:427-428 */
-  int32_t max_batch;                  /* queries per call */
-  int32_t max_beams;
+  int32_t max_batch;                  /* capacities of the workspaces (see rb200_engine_resize): queries per call, */
+  int32_t max_beams;                  /* beams per query, */
   int32_t max_src_len;                /* padded query length S */
   int32_t precision;                  /* rb200_precision */
   int32_t device;
@@ -158,6 +205,9 @@ typedef struct {
 
 int rb200_engine_create(const rb200_engine_config* cfg, rb200_engine** out);
 int rb200_engine_free(rb200_engine* eng);
+/* Re-allocate the shape-dependent workspaces (activations, KV cache, beam state) for new capacities; the packed
+ * weights stay. Every call below accepts any batch <= max_batch, num_beams <= max_beams, S <= max_src_len. */
+int rb200_engine_resize(rb200_engine* eng, int max_batch, int max_beams, int max_src_len);
 /* Hand one fp32 tensor of the HF state dict to the engine by its state-dict key,
  * e.g. "decoder.block.3.layer.1.EncDecAttention.q.weight", "list_output_embeds.7.weight",
  * "start_token_embed". data_dev is a device pointer to contiguous fp32 in the HF layout; the engine
@@ -193,13 +243,33 @@ int rb200_engine_encoder_states(const rb200_engine* eng, const float** states_de
 int rb200_engine_decode_step(rb200_engine* eng, const rb200_beam* beam, int t, float* logits_dev, void* stream);
 /* the beam state the engine owns (created for max_batch x max_beams). */
 int rb200_engine_beam(rb200_engine* eng, rb200_beam** beam);
+/* fp32 [max_batch*max_beams, d_model] buffer rb200_engine_decode_step takes its inputs from for t >= 1: pass it as
+ * next_x_dev to rb200_beam_step (rows at beam-row ids). */
+int rb200_engine_next_input(const rb200_engine* eng, float** next_x_dev);
+/* Teacher-forced decoder pass over GIVEN DocID tokens, no beam search: the model forward the reference runs when it
+ * is handed decoder_input_ids (t5_generative_retriever.py:295-450) and the sum rerank_forward takes over it
+ * (:794-798). tokens_dev int32 [batch*rows_per_query, T]: tokens[r][p] is the code at position p of row r's DocID;
+ * position p's decoder input is the start embedding (p = 0) or list_decoder_embeds[p-1][tokens[r][p-1]]. Outputs, each
+ * optional (NULL), all POSITION-MAJOR with R = batch*rows_per_query rows per position:
+ *   logits_dev fp32 [T, R, V]        = the reference's `logits` list (position p with the p-th output table),
+ *   hidden_dev fp32 [T, R, d_model]  = decoder_last_hidden_state (after the final layer norm and the optional d^-1/2),
+ *   scores_dev fp32 [R]              = sum_p logits[p][r][tokens[r][p]]   (= rerank_forward's score).
+ * The rows of a query share its encoder pass. T <= 32. */
+int rb200_engine_forward(rb200_engine* eng, const int64_t* input_ids_dev, const int64_t* attention_mask_dev, int batch,
+                         int S, int rows_per_query, const int32_t* tokens_dev, int T, float* logits_dev,
+                         float* hidden_dev, float* scores_dev, void* stream);
 /* number of kernel launches issued by the last rb200_engine_search* call. */
 int64_t rb200_engine_last_launch_count(const rb200_engine* eng);
-/* Forced tail: once every beam of a batch sits on a single trie leaf, the rest of its DocID is determined, and the
- * engine evaluates the remaining positions of all beams in one teacher-forced pass (same per-row arithmetic as the
- * step loop of generation.py:423-530, far fewer and larger kernels). Returns the decode step at which the last
- * search switched, or -1 if it ran step by step to the end (RB200_TAIL=0 disables the switch). */
+/* Forced tail: once every beam of a QUERY sits on a single trie leaf, the rest of its DocIDs is determined; the query
+ * leaves the step loop and the remaining positions of all such queries are evaluated in one teacher-forced pass after
+ * the loop (same per-row arithmetic as the steps of generation.py:423-530 they replace, far fewer and larger
+ * kernels). Returns the first step at which a query of the last search was frozen, or -1 if every query ran step by
+ * step to the end (RB200_TAIL=0 disables freezing). */
 int rb200_engine_last_tail_step(const rb200_engine* eng);
+/* frozen_at_host[t] (t < n) = queries of the last search frozen after t steps; *tail_rows_host = rows of its
+ * forced-tail pass (sum over frozen queries of num_beams * remaining positions). */
+int rb200_engine_last_freeze_histogram(const rb200_engine* eng, int32_t* frozen_at_host, int n,
+                                       int64_t* tail_rows_host);
 /* Measurement aid for bench.py's roofline leg: with profiling on, every GEMM launch of the engine is
  * bracketed by CUDA events on its stream. get_profile synchronises and returns the summed GEMM device time
  * (ms), the algorithmic FLOPs (2*M*N*K per launch) and the launch count since profiling was switched on. */

@@ -188,3 +188,36 @@ def literal_beam_search(model, processor, batch_size, num_beams, max_new_tokens,
             pad_token_id=0, eos_token_id=1, output_scores=True, return_dict_in_generate=True,
             synced_gpus=False, apply_log_softmax_for_scores=apply_log_softmax_for_scores, **kwargs)
     return out
+
+
+_legacy = None
+
+
+def load_reference_legacy_trie():
+    """Import /root/reference/t5_pretrainer/utils/generation_utils.py in place: the nested-dict ``Trie`` (:9-90) and
+    ``PrefixConstrainedLogitsProcessorForSmtidTree`` (:92-124, -inf mask, eos fallback) that predate the sparse
+    processor. Used as the third voice of the allowed-token cross-check (SURVEY 8c golden item 2)."""
+    global _legacy
+    if _legacy is not None:
+        return _legacy
+    path = os.path.join(os.path.dirname(os.path.dirname(_GEN_PATH)), "utils", "generation_utils.py")
+    if not os.path.isfile(path):
+        raise FileNotFoundError(path)
+    lp = sys.modules.get("transformers.generation_logits_process")
+    if lp is None:
+        lp = types.ModuleType("transformers.generation_logits_process")
+        sys.modules["transformers.generation_logits_process"] = lp
+    if not hasattr(lp, "LogitsProcessor"):
+        lp.LogitsProcessor = type("LogitsProcessor", (), {})
+    if not hasattr(lp, "LogitsProcessorList"):
+        lp.LogitsProcessorList = _LogitsProcessorList
+    if "ujson" not in sys.modules:
+        m = types.ModuleType("ujson")
+        m.__dict__.update(load=json.load, loads=json.loads, dump=json.dump, dumps=json.dumps)
+        sys.modules["ujson"] = m
+    spec = importlib.util.spec_from_file_location("_ripor_reference_generation_utils", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    _legacy = mod
+    return mod
+

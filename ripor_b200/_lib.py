@@ -41,6 +41,16 @@ SIGNATURES = {
     "rb200_trie_level_counts": (C.c_int, [c_void_p, c_void_p]),
     "rb200_trie_save": (C.c_int, [c_void_p, c_char_p]),
     "rb200_trie_load": (C.c_int, [c_char_p, P(c_void_p)]),
+    "rb200_trie_save_tagged": (C.c_int, [c_void_p, c_char_p, C.c_uint64]),
+    "rb200_trie_load_tagged": (C.c_int, [c_char_p, P(C.c_uint64), P(c_void_p)]),
+    "rb200_trie_leaf_expand": (C.c_int, [c_void_p, c_void_p, c_i64, C.c_int, c_void_p, c_void_p, c_void_p]),
+    "rb200_docid_json_open": (C.c_int, [c_char_p, C.c_int, P(c_void_p)]),
+    "rb200_docid_json_free": (C.c_int, [c_void_p]),
+    "rb200_docid_json_info": (C.c_int, [c_void_p, P(c_i64), P(c_i32), P(c_i32), P(c_i64)]),
+    "rb200_docid_json_codes": (C.c_int, [c_void_p, P(c_void_p)]),
+    "rb200_docid_json_keys": (C.c_int, [c_void_p, P(c_void_p), P(c_void_p)]),
+    "rb200_trie_build_from_table": (C.c_int, [c_void_p, C.c_int, C.c_int, P(c_void_p)]),
+    "rb200_unpack_codes": (C.c_int, [c_void_p, c_i64, c_i64, C.c_int, C.c_int, c_void_p]),
     "rb200_trie_mask_host": (C.c_int, [c_void_p, c_void_p, c_i64, C.c_int, c_void_p]),
     "rb200_trie_leaf_docs": (C.c_int, [c_void_p, c_i64, P(c_void_p), P(c_i64)]),
     "rb200_trie_find_leaf": (C.c_int, [c_void_p, c_void_p, P(c_i64)]),
@@ -49,6 +59,8 @@ SIGNATURES = {
     "rb200_beam_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, P(c_void_p)]),
     "rb200_beam_free": (C.c_int, [c_void_p]),
     "rb200_beam_reset": (C.c_int, [c_void_p, c_void_p, C.c_int, c_void_p]),
+    "rb200_beam_reset_beams": (C.c_int, [c_void_p, c_void_p, C.c_int, C.c_int, c_void_p]),
+    "rb200_beam_forced_tail": (C.c_int, [c_void_p, c_void_p, C.c_int, c_void_p, C.c_int, c_void_p]),
     "rb200_beam_step": (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, c_void_p, c_void_p, C.c_int,
                                   c_void_p]),
     "rb200_beam_finalize": (C.c_int, [c_void_p, c_void_p, C.c_int, c_f64, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -56,6 +68,11 @@ SIGNATURES = {
     "rb200_beam_current_step": (C.c_int, [c_void_p]),
     "rb200_engine_create": (C.c_int, [P(EngineConfig), P(c_void_p)]),
     "rb200_engine_free": (C.c_int, [c_void_p]),
+    "rb200_engine_resize": (C.c_int, [c_void_p, C.c_int, C.c_int, C.c_int]),
+    "rb200_engine_next_input": (C.c_int, [c_void_p, P(c_void_p)]),
+    "rb200_engine_forward": (C.c_int, [c_void_p, c_void_p, c_void_p, C.c_int, C.c_int, C.c_int, c_void_p, C.c_int,
+                                       c_void_p, c_void_p, c_void_p, c_void_p]),
+    "rb200_engine_last_freeze_histogram": (C.c_int, [c_void_p, c_void_p, C.c_int, P(c_i64)]),
     "rb200_engine_set_weight": (C.c_int, [c_void_p, c_char_p, c_void_p, c_i64, c_void_p]),
     "rb200_engine_finalize_weights": (C.c_int, [c_void_p, c_void_p]),
     "rb200_engine_workspace_bytes": (c_i64, [c_void_p]),

@@ -44,6 +44,12 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------------------
 // self-attention against the KV cache
 // ------------------------------------------------------------------------------------------------------------
+// compact row m of the step loop -> original row id (query id when one row per query runs, i.e. step 0)
+__device__ __forceinline__ int orig_row(const SelfAttnArgs& a, int m) {
+  if (a.qlist == nullptr) return m;
+  return a.rpq == 1 ? a.qlist[m] : a.qlist[m / a.nb] * a.nb + m % a.nb;
+}
+
 __global__ void __launch_bounds__(kWarps * 32, 5) self_attn_warp_kernel(SelfAttnArgs a, ActOut ctx) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;
@@ -52,10 +58,11 @@ __global__ void __launch_bounds__(kWarps * 32, 5) self_attn_warp_kernel(SelfAttn
   pdl_wait();
   if (m >= a.M) return;
   const int inner = a.H * 64, t = a.t, L = a.L;
-  const int arow = (a.rpq == 1) ? m * a.nb : m;
+  const int orow = orig_row(a, m);                                  // cache slots / ancestry: original row ids
+  const int arow = (a.rpq == 1) ? orow * a.nb : orow;
   const float* qrow = a.qkv + (int64_t)m * 3 * inner + h * 64;
   {
-    const int64_t dst = ((int64_t)t * a.row_cap + m) * inner + h * 64 + lane * 2;
+    const int64_t dst = ((int64_t)t * a.row_cap + orow) * inner + h * 64 + lane * 2;
     *reinterpret_cast<float2*>(a.cache_k + dst) = *reinterpret_cast<const float2*>(qrow + inner + lane * 2);
     *reinterpret_cast<float2*>(a.cache_v + dst) = *reinterpret_cast<const float2*>(qrow + 2 * inner + lane * 2);
   }
@@ -146,7 +153,8 @@ __global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArg
   // scheduling than the short early steps take to compute)
   for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += gridDim.x * kWarps) {
   const int m = wid / a.H, h = wid - m * a.H;
-  const int arow = (a.rpq == 1) ? m * a.nb : m;
+  const int orow = orig_row(a, m);
+  const int arow = (a.rpq == 1) ? orow * a.nb : orow;
   const float* qrow = a.qkv + (int64_t)m * 3 * inner + h * 64;     // q | k | v of this row at position t
   __syncwarp();                                                     // the previous task's readers are done
   if (lane < 16) cp_async16_on(qs + lane * 4, qrow + lane * 4);
@@ -216,7 +224,7 @@ __global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArg
   }
   // this position's K/V go to cache slot (t, m) for the later steps: 64 floats per head, one float2 per lane
   {
-    const int64_t dst = ((int64_t)t * a.row_cap + m) * inner + h * 64 + lane * 2;
+    const int64_t dst = ((int64_t)t * a.row_cap + orow) * inner + h * 64 + lane * 2;
     *reinterpret_cast<float2*>(a.cache_k + dst) = *reinterpret_cast<const float2*>(qrow + inner + lane * 2);
     *reinterpret_cast<float2*>(a.cache_v + dst) = *reinterpret_cast<const float2*>(qrow + 2 * inner + lane * 2);
   }
@@ -240,12 +248,15 @@ __global__ void __launch_bounds__(kWarps * 32, 2) self_attn_tail_kernel(TailAttn
   float* vs = ks + 32 * 64;
   float* qs = vs + 32 * 64;
   float* es = qs + 32 * 64;
-  const int inner = a.H * 64, t = a.t, T = a.T, L = a.L, R = a.R;
-  const int P = t + T;                                              // positions of the finished lineage (<= 32)
-  const int ntask = R * a.H;
+  const int inner = a.H * 64, L = a.L;
+  const int P = a.lay.P;                                            // positions of the finished lineage (<= 32)
+  const int ntask = a.R * a.H;
   pdl_wait();
   for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += gridDim.x * kWarps) {
-    const int r = wid / a.H, h = wid - r * a.H;
+    const int rp = wid / a.H, h = wid - rp * a.H;                   // frozen row (freeze order), head
+    const int bq = a.fz_list[rp / a.nb];
+    const int r = bq * a.nb + rp % a.nb;                            // original row id
+    const int t = a.qstart ? a.qstart[bq] : 0, T = P - t;           // this row's pass: positions t..P-1
     __syncwarp();
     // ---- stage K, V of every position and q of the T new ones ------------------------------------------------------
     const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
@@ -259,7 +270,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) self_attn_tail_kernel(TailAttn
           kp = a.cache_k + (int64_t)slot * inner + h * 64 + l16 * 4;
           vp = a.cache_v + (int64_t)slot * inner + h * 64 + l16 * 4;
         } else {
-          const float* row = a.qkv + ((int64_t)(p - t) * R + r) * 3 * inner + h * 64 + l16 * 4;
+          const float* row = a.qkv + ((int64_t)a.lay.off[p] + rp) * 3 * inner + h * 64 + l16 * 4;
           kp = row + inner;
           vp = row + 2 * inner;
           cp_async16_on(qs + (p - t) * 64 + l16 * 4, row);
@@ -323,7 +334,7 @@ __global__ void __launch_bounds__(kWarps * 32, 2) self_attn_tail_kernel(TailAttn
 #pragma unroll
       for (int u = 0; u < kTailJB; ++u)
         if (j0 + u < T)
-          act_store2(ctx, ((int64_t)(j0 + u) * R + r) * inner + h * 64 + lane * 2,
+          act_store2(ctx, ((int64_t)a.lay.off[t + j0 + u] + rp) * inner + h * 64 + lane * 2,
                      make_float2(o2[u].x * inv[u], o2[u].y * inv[u]));
     }
   }
@@ -364,20 +375,25 @@ __global__ void __launch_bounds__(x_warps<QS, XB>() * 32, 1) cross_attn_warp_ker
   float* es = vs + 32 * 64;
   float* qs = es + kXB * 32;                                       // two buffers of XB rows (QS only)
   const int wid = blockIdx.x * kXWarps + warp;
-  const int b = wid / a.H, h = wid - b * a.H;
+  const int b = wid / a.H, h = wid - b * a.H;                      // query slot (compact / freeze order), head
   const int rpq = a.rows_per_query, S = a.S;
   pdl_wait();
   if (b * rpq >= a.M) return;
+  const int bq = a.qmap ? a.qmap[b] : b;                           // the query whose encoder K/V and mask to use
+  const int t0 = (a.ragged && a.qstart) ? a.qstart[bq] : 0;
+  const int nblocks = a.ragged ? a.lay.P - t0 : a.nblocks;
   const int inner = a.H * 64;
   const int i0 = blockIdx.y * kXB;
   const int nact = min(kXB, rpq - i0);
-  const int64_t* mk = a.mask + (int64_t)b * S;
+  const int64_t* mk = a.mask + (int64_t)bq * S;
   const int64_t q_ld = a.q_ld ? a.q_ld : inner;
   // this lane's source pointer for staging: row (half) of the chunk, 16-byte column l16; advances 2 rows per step
-  const float* kv_lane = a.kv + ((int64_t)b * S + half) * a.ld + h * 64 + l16 * 4;
+  const float* kv_lane = a.kv + ((int64_t)bq * S + half) * a.ld + h * 64 + l16 * 4;
   const int64_t step2 = 2 * a.ld;
   const bool resident = S <= 32;       // one chunk: the staged K/V serve every position block of the forced tail
-  auto row_of = [&](int z) { return (int64_t)z * a.block_rows + (int64_t)b * rpq + i0; };
+  auto row_of = [&](int z) {
+    return (a.ragged ? (int64_t)a.lay.off[t0 + z] : (int64_t)z * a.block_rows) + (int64_t)b * rpq + i0;
+  };
   auto stage_q = [&](int z, float* dst) {                          // q rows of block z; rows beyond nact repeat row 0
     const float* qb = a.q + row_of(z) * q_ld + h * 64 + l16 * 4;
 #pragma unroll
@@ -387,15 +403,15 @@ __global__ void __launch_bounds__(x_warps<QS, XB>() * 32, 1) cross_attn_warp_ker
     }
   };
   const int z0 = blockIdx.z, zs = gridDim.z;
-  if (QS) stage_q(z0, qs);
+  if (QS && z0 < nblocks) stage_q(z0, qs);
   asm volatile("cp.async.commit_group;" ::: "memory");
   int qbuf = 0;
-  for (int z = z0; z < a.nblocks; z += zs, qbuf ^= 1) {
+  for (int z = z0; z < nblocks; z += zs, qbuf ^= 1) {
     const int64_t row0 = row_of(z);
     const float* qcur = qs + qbuf * (kXB * 64);
     const float* qg = a.q + row0 * q_ld + h * 64;
     __syncwarp();                                                  // the previous block's readers are done
-    if (QS && z + zs < a.nblocks) stage_q(z + zs, qs + (qbuf ^ 1) * (kXB * 64));   // prefetch the next block's q
+    if (QS && z + zs < nblocks) stage_q(z + zs, qs + (qbuf ^ 1) * (kXB * 64));     // prefetch the next block's q
     asm volatile("cp.async.commit_group;" ::: "memory");           // (possibly empty: uniform group accounting)
     float run_max[kXB], run_sum[kXB];
     float2 o2[kXB];
@@ -445,7 +461,7 @@ __global__ void __launch_bounds__(x_warps<QS, XB>() * 32, 1) cross_attn_warp_ker
         }
       }
       if (a.rel_bias != nullptr && ok) {   // encoder: query row i0 + i of the sequence, key p
-        const float* rb_h = a.rel_bias + (int64_t)h * (2 * S - 1) + (p + S - 1 - i0);
+        const float* rb_h = a.rel_bias + (int64_t)h * (2 * a.rel_S - 1) + (p + a.rel_S - 1 - i0);
 #pragma unroll
         for (int i = 0; i < kXB; ++i)
           if (i < nact) sc[i] += __ldg(rb_h - i);
@@ -517,11 +533,13 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma_kernel(CrossAttnArgs a,
   __shared__ unsigned valid_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.x / a.H, h = blockIdx.x - b * a.H;
+  const int b = blockIdx.x / a.H, h = blockIdx.x - b * a.H;        // query slot, head
   const int S = a.S, rpq = a.rows_per_query, inner = a.H * 64;
   pdl_wait();
+  const int bq = a.qmap ? a.qmap[b] : b;
+  const int t0 = (a.ragged && a.qstart) ? a.qstart[bq] : 0;
   // ---- K, V of this (query, head): split into tf32 planes once; masked / absent keys are zero rows --------------
-  const int64_t* mk = a.mask + (int64_t)b * S;
+  const int64_t* mk = a.mask + (int64_t)bq * S;
   if (warp == 0) {
     const bool ok = lane < S && mk[lane < S ? lane : 0] != 0;
     const unsigned bits = __ballot_sync(0xffffffffu, ok);
@@ -529,7 +547,7 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma_kernel(CrossAttnArgs a,
   }
   __syncthreads();
   const unsigned valid = valid_s;
-  const float* kvb = a.kv + (int64_t)b * S * a.ld + h * 64;
+  const float* kvb = a.kv + (int64_t)bq * S * a.ld + h * 64;
   for (int e = threadIdx.x; e < 32 * 16; e += blockDim.x) {
     const int key = e >> 4, c4 = (e & 15) * 4;
     float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
@@ -549,9 +567,11 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma_kernel(CrossAttnArgs a,
   }
   __syncthreads();
   // ---- 16-row tiles of this query's rows: tile row q <-> (position block q / rpq, beam q % rpq) ------------------
-  const int nrows = a.nblocks * rpq;
+  const int nrows = (a.ragged ? a.lay.P - t0 : a.nblocks) * rpq;
   const int64_t q_ld = a.q_ld ? a.q_ld : inner;
-  auto global_row = [&](int q) { return (int64_t)(q / rpq) * a.block_rows + (int64_t)b * rpq + (q % rpq); };
+  auto global_row = [&](int q) {
+    return (a.ragged ? (int64_t)a.lay.off[t0 + q / rpq] : (int64_t)(q / rpq) * a.block_rows) + (int64_t)b * rpq + (q % rpq);
+  };
   for (int tile = warp; tile * 16 < nrows; tile += 4) {
     const int q0 = tile * 16 + g, q1 = q0 + 8;                      // this lane's two rows of the tile
     const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64;
@@ -694,11 +714,13 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
   __shared__ unsigned valid_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  const int b = blockIdx.x / a.H, h = blockIdx.x - b * a.H;
+  const int b = blockIdx.x / a.H, h = blockIdx.x - b * a.H;        // query slot, head
   const int S = a.S, rpq = a.rows_per_query, inner = a.H * 64;
   bool bad = false;
   pdl_wait();
-  const int64_t* mk = a.mask + (int64_t)b * S;
+  const int bq = a.qmap ? a.qmap[b] : b;
+  const int t0 = (a.ragged && a.qstart) ? a.qstart[bq] : 0;
+  const int64_t* mk = a.mask + (int64_t)bq * S;
   if (warp == 0) {
     const bool ok = lane < S && mk[lane < S ? lane : 0] != 0;
     const unsigned bits = __ballot_sync(0xffffffffu, ok);
@@ -706,7 +728,7 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
   }
   __syncthreads();
   const unsigned valid = valid_s;
-  const float* kvb = a.kv + (int64_t)b * S * a.ld + h * 64;
+  const float* kvb = a.kv + (int64_t)bq * S * a.ld + h * 64;
   for (int e = threadIdx.x; e < 32 * 16; e += blockDim.x) {
     const int key = e >> 4, c4 = (e & 15) * 4;
     float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
@@ -725,9 +747,11 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
     *reinterpret_cast<uint2*>(v_lo + key * kKLd + c4) = make_uint2(l0, l1);
   }
   __syncthreads();
-  const int nrows = a.nblocks * rpq;
+  const int nrows = (a.ragged ? a.lay.P - t0 : a.nblocks) * rpq;
   const int64_t q_ld = a.q_ld ? a.q_ld : inner;
-  auto global_row = [&](int q) { return (int64_t)(q / rpq) * a.block_rows + (int64_t)b * rpq + (q % rpq); };
+  auto global_row = [&](int q) {
+    return (a.ragged ? (int64_t)a.lay.off[t0 + q / rpq] : (int64_t)(q / rpq) * a.block_rows) + (int64_t)b * rpq + (q % rpq);
+  };
   const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
   const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
   const int vrow = (lane & 7) + 8 * ((lane >> 3) & 1), vcol = 8 * (lane >> 4);   // ldmatrix row of this lane
@@ -853,13 +877,16 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(Ta
   const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
   const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
   const int vrow = (lane & 7) + 8 * ((lane >> 3) & 1), vcol = 8 * (lane >> 4);   // ldmatrix row of this lane
-  const int inner = a.H * 64, t = a.t, T = a.T, L = a.L, R = a.R;
-  const int P = t + T;
-  const int ntask = R * a.H;
+  const int inner = a.H * 64, L = a.L;
+  const int P = a.lay.P;
+  const int ntask = a.R * a.H;
   bool bad = false;
   pdl_wait();
   for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += gridDim.x * kWarps) {
-    const int r = wid / a.H, h = wid - r * a.H;
+    const int rp = wid / a.H, h = wid - rp * a.H;                   // frozen row (freeze order), head
+    const int bq = a.fz_list[rp / a.nb];
+    const int r = bq * a.nb + rp % a.nb;                            // original row id
+    const int t = a.qstart ? a.qstart[bq] : 0, T = P - t;           // this row's pass: positions t..P-1
     __syncwarp();                                                   // the previous task's fragment reads are done
     // ---- stage and split K, V of positions 0..P-1 (rows >= P: zeros) -------------------------------------------
     const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
@@ -873,7 +900,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(Ta
           kk = *reinterpret_cast<const float4*>(a.cache_k + (int64_t)slot * inner + h * 64 + l16 * 4);
           vv = *reinterpret_cast<const float4*>(a.cache_v + (int64_t)slot * inner + h * 64 + l16 * 4);
         } else {
-          const float* row = a.qkv + ((int64_t)(p - t) * R + r) * 3 * inner + h * 64 + l16 * 4;
+          const float* row = a.qkv + ((int64_t)a.lay.off[p] + rp) * 3 * inner + h * 64 + l16 * 4;
           kk = *reinterpret_cast<const float4*>(row + inner);
           vv = *reinterpret_cast<const float4*>(row + 2 * inner);
         }
@@ -892,8 +919,8 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(Ta
     // ---- the T queries as 16-row tiles: tile row q = query index (position t + q) --------------------------------
     for (int tile = 0; tile * 16 < T; ++tile) {
       const int q0 = tile * 16 + g, q1 = q0 + 8;
-      const float* qr0 = a.qkv + ((int64_t)min(q0, T - 1) * R + r) * 3 * inner + h * 64 + 2 * t4;
-      const float* qr1 = a.qkv + ((int64_t)min(q1, T - 1) * R + r) * 3 * inner + h * 64 + 2 * t4;
+      const float* qr0 = a.qkv + ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+      const float* qr1 = a.qkv + ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
       float sacc[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
@@ -978,13 +1005,13 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(Ta
       }
       const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
       if (q0 < T) {
-        const int64_t base = ((int64_t)q0 * R + r) * inner + h * 64 + 2 * t4;
+        const int64_t base = ((int64_t)a.lay.off[t + q0] + rp) * inner + h * 64 + 2 * t4;
 #pragma unroll
         for (int nd = 0; nd < 8; ++nd)
           act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
       }
       if (q1 < T) {
-        const int64_t base = ((int64_t)q1 * R + r) * inner + h * 64 + 2 * t4;
+        const int64_t base = ((int64_t)a.lay.off[t + q1] + rp) * inner + h * 64 + 2 * t4;
 #pragma unroll
         for (int nd = 0; nd < 8; ++nd)
           act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
@@ -1044,7 +1071,8 @@ static cudaError_t launch_cross_cfg(const CrossAttnArgs& a, ActOut ctx, cudaStre
   // position blocks of the forced tail: walked inside the kernel when the staged K/V can stay resident (S <= 32),
   // one grid slice per block otherwise
   constexpr int kXWarps = x_warps<QS, XB>();
-  const dim3 grid(ceil_div((int64_t)B * a.H, kXWarps), ceil_div(a.rows_per_query, XB), a.S <= 32 ? 1 : a.nblocks),
+  const dim3 grid(ceil_div((int64_t)B * a.H, kXWarps), ceil_div(a.rows_per_query, XB),
+                  a.S <= 32 ? 1 : (a.ragged ? a.lay.P : a.nblocks)),
       block(kXWarps * 32);
   constexpr size_t smem = (size_t)kXWarps * x_warp_floats<QS, XB>() * sizeof(float);
   static_assert(smem <= 227 * 1024, "cross-attention staging exceeds the shared memory of an SM");
@@ -1059,7 +1087,8 @@ static cudaError_t launch_cross_cfg(const CrossAttnArgs& a, ActOut ctx, cudaStre
 }
 
 int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s) {
-  RB_REQUIRE(a.t >= 1 && a.T >= 1 && a.t + a.T <= 32, "forced tail needs 1 <= t and t + T <= 32 (t=%d, T=%d)", a.t, a.T);
+  RB_REQUIRE(a.lay.P >= 1 && a.lay.P <= RB_TAIL_MAX_L, "forced tail needs 1 <= P <= %d (P=%d)", RB_TAIL_MAX_L, a.lay.P);
+  if (a.R == 0) return 0;
   static const bool use_mma = []() {
     const char* e = getenv("RB200_SELF_MMA");
     return !(e && e[0] == '0');
@@ -1094,7 +1123,8 @@ bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, 
   }();
   // many rows per (query, head) against <= 32 keys (the forced tail): tensor-core kernel
   // (the exact fp32 mode keeps the FFMA kernel)
-  if (use_mma && ctx.mode != 0 && a.S <= 32 && a.rel_bias == nullptr && (int64_t)a.nblocks * a.rows_per_query >= 32) {
+  if (use_mma && ctx.mode != 0 && a.S <= 32 && a.rel_bias == nullptr &&
+      (a.ragged || (int64_t)a.nblocks * a.rows_per_query >= 32)) {
     const int B = a.M / a.rows_per_query;
     const cudaError_t err = prec_is_fp16(ctx.mode)
                                 ? launch_pdl(cross_attn_mma16_kernel, dim3(B * a.H), dim3(128), 0, s, a, ctx)

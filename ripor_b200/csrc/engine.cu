@@ -36,12 +36,12 @@ struct Layer {
 
 }  // namespace
 
-// One lane = the workspaces of one independent batch in flight. Queries never interact, so a large batch is split
-// over two lanes that run on two streams: while one lane drains a GEMM (epilogue, launch gap, a 60-of-74-SM-pair
-// tail) or sits in an HBM-bound attention kernel, the other lane's kernels fill the idle SMs / tensor pipes.
+// The workspaces of one batch in flight. (Round 1 also had a second lane on a second stream for half of the batch;
+// measured slower on B200 - the GEMMs are bound by operand delivery, not by idle SMs - and removed.)
 struct Lane {
   int64_t Mcap = 0, Rcap = 0, BScap = 0;
   float* x = nullptr;              // [Mcap, d] residual stream
+  float* x_full = nullptr;         // [Rcap, d] next decoder inputs of every beam row, at original row ids
   void* xn = nullptr;              // ActBuf [planes][Mcap][d]
   float* qkv = nullptr;            // [Mcap, 3*inner]
   float* q2 = nullptr;             // [Mcap, inner]
@@ -54,8 +54,6 @@ struct Lane {
   float* cache_v = nullptr;
   float* ss[2] = {nullptr, nullptr};   // NormFold: [Mcap, np] per-row partial sums of x^2, two norm points alive
   rb200_beam* beam = nullptr;
-  cudaStream_t own_stream = nullptr;   // lane 1 only
-  cudaEvent_t done = nullptr;
   // batch in flight
   int B = 0, S = 0, nb = 0;
   const int64_t* cur_mask = nullptr;
@@ -84,15 +82,13 @@ struct rb200_engine {
   bool fold = false;
   int np = 0;
   std::vector<Stash> stash;
-  Lane lanes[2];                   // lane 0: full capacity; lane 1: the second half of a split batch
-  int num_lanes = 1;
-  cudaEvent_t fork = nullptr;
+  Lane lanes[1];
   int64_t* ids_dev = nullptr;      // host-call staging
   int64_t* mask_dev = nullptr;
   int64_t* seq_dev = nullptr;
   float* score_dev = nullptr;
   int32_t* leaf_dev = nullptr;
-  int64_t ws_bytes = 0;
+  int64_t ws_bytes = 0, ws_only_bytes = 0;
   int64_t launches = 0;
   // optional per-GEMM event timing (rb200_engine_set_profiling)
   bool profiling = false;
@@ -104,8 +100,11 @@ struct rb200_engine {
   // forced tail (beam.h): once every beam sits on a single trie leaf, the remaining positions run as one pass
   bool tail = false;
   float** in_tab_dev = nullptr;    // [Lmodel] device copy of in_tab
-  int32_t* flag_host = nullptr;    // pinned
-  int last_tail_from = -1;         // step at which the last search switched to the forced tail (-1: never)
+  int32_t* flag_host = nullptr;    // pinned [2]: {queries still stepping, queries frozen} after a beam step
+  int last_tail_from = -1;         // first step at which a query of the last search was frozen (-1: none)
+  int frozen_at[RB_TAIL_MAX_L + 1] = {0};   // last search: queries frozen after t steps
+  int64_t last_tail_rows = 0;      // rows of the last forced-tail pass
+  int ws_batch = 0, ws_beams = 0, ws_src = 0;   // capacities of the current workspaces
 
   ActOut act(const Lane& l, void* base, int64_t row_len) const {
     return ActOut{base, l.Mcap * row_len, mode, overflow};
@@ -197,17 +196,18 @@ int build_bias_tables(rb200_engine* e, int S, cudaStream_t s) {
     RB_CUDA(cudaMemcpyAsync(e->dec_bias, t.data(), t.size() * 4, cudaMemcpyHostToDevice, s));
     RB_CUDA(cudaStreamSynchronize(s));
   }
-  if (S > 0 && S != e->enc_bias_S) {
-    std::vector<float> t((size_t)e->H * (2 * S - 1));
+  if (S > 0 && e->enc_bias_S != c.max_src_len) {
+    // indexed by (key - query) + Smax - 1 for the workspace's max_src_len: valid for every batch's padded length
+    const int Sm = c.max_src_len;
+    std::vector<float> t((size_t)e->H * (2 * Sm - 1));
     for (int h = 0; h < e->H; ++h)
-      for (int off = 0; off < 2 * S - 1; ++off)
-        t[(size_t)h * (2 * S - 1) + off] =
-            e->enc_rel_host[(size_t)rb::relative_bucket(off - (S - 1), true, c.num_buckets, c.max_distance) * e->H + h];
-    if (e->enc_bias == nullptr)
-      RB_TRY(dev_alloc(e, (void**)&e->enc_bias, (int64_t)e->H * (2 * c.max_src_len - 1) * 4));
+      for (int off = 0; off < 2 * Sm - 1; ++off)
+        t[(size_t)h * (2 * Sm - 1) + off] =
+            e->enc_rel_host[(size_t)rb::relative_bucket(off - (Sm - 1), true, c.num_buckets, c.max_distance) * e->H + h];
+    if (e->enc_bias == nullptr) RB_CUDA(cudaMalloc((void**)&e->enc_bias, (size_t)e->H * (2 * Sm - 1) * 4));
     RB_CUDA(cudaMemcpyAsync(e->enc_bias, t.data(), t.size() * 4, cudaMemcpyHostToDevice, s));
     RB_CUDA(cudaStreamSynchronize(s));
-    e->enc_bias_S = S;
+    e->enc_bias_S = Sm;
   }
   return 0;
 }
@@ -229,6 +229,8 @@ static float half_bits_to_float(uint16_t h) {
 }
 
 static int engine_build(rb200_engine* e, const rb200_engine_config* cfg);
+static int alloc_workspace(rb200_engine* e, int max_batch, int max_beams, int max_src_len);
+static void free_workspace(rb200_engine* e);
 
 extern "C" {
 
@@ -309,54 +311,67 @@ static int engine_build(rb200_engine* e, const rb200_engine_config* cfg) {
   }
   {
     const char* tl = getenv("RB200_TAIL");
-    e->tail = e->Lmodel <= 32 && !(tl && tl[0] == '0');
-    RB_CUDA(cudaMallocHost((void**)&e->flag_host, sizeof(int32_t)));
+    e->tail = !(tl && tl[0] == '0');
+    RB_CUDA(cudaMallocHost((void**)&e->flag_host, 2 * sizeof(int32_t)));
   }
-  // workspaces: lane 0 can hold a whole batch, lane 1 the second half of a split one
-  const int64_t pe = (int64_t)e->planes * e->elem;
-  {
-    const char* env = getenv("RB200_LANES");
-    // measured on B200 (bench workload): two lanes 2507 q/s vs one lane 2562 q/s - the GEMMs are already bound by
-    // L2->SM operand delivery, so overlapping a second batch only adds contention. Opt-in with RB200_LANES=2.
-    e->num_lanes = (cfg->max_batch >= 2 && env && env[0] == '2') ? 2 : 1;
-  }
-  for (int li = 0; li < e->num_lanes; ++li) {
-    Lane& l = e->lanes[li];
-    const int lane_batch = li == 0 ? cfg->max_batch : cfg->max_batch / 2;
-    l.Rcap = (int64_t)lane_batch * cfg->max_beams;
-    l.BScap = (int64_t)lane_batch * cfg->max_src_len;
-    // the forced tail runs up to Lmodel positions of every beam row in one pass (lane 0 only)
-    l.Mcap = std::max((li == 0 && e->tail) ? l.Rcap * e->Lmodel : l.Rcap, l.BScap);
-    RB_TRY(dev_alloc(e, (void**)&l.x, l.Mcap * d * 4));
-    RB_TRY(dev_alloc(e, &l.xn, l.Mcap * d * pe));
-    RB_TRY(dev_alloc(e, (void**)&l.qkv, l.Mcap * 3 * inner * 4));
-    RB_TRY(dev_alloc(e, (void**)&l.q2, l.Mcap * inner * 4));
-    RB_TRY(dev_alloc(e, &l.ctx, l.Mcap * inner * pe));
-    RB_TRY(dev_alloc(e, &l.hbuf, l.Mcap * dff * pe));
-    RB_TRY(dev_alloc(e, (void**)&l.logits, ((li == 0 && e->tail) ? l.Mcap : l.Rcap) * e->V * 4));
-    RB_TRY(dev_alloc(e, (void**)&l.cross_kv, l.BScap * cfg->num_decoder_layers * 2 * inner * 4));
-    RB_TRY(dev_alloc(e, (void**)&l.enc_out, l.BScap * d * 4));
-    const int64_t cache = (int64_t)cfg->num_decoder_layers * e->Lmodel * l.Rcap * inner * 4;
-    RB_TRY(dev_alloc(e, (void**)&l.cache_k, cache));
-    RB_TRY(dev_alloc(e, (void**)&l.cache_v, cache));
-    for (int b = 0; b < 2; ++b) RB_TRY(dev_alloc(e, (void**)&l.ss[b], l.Mcap * std::max(e->np, 1) * 4));
-    // planes of the activation buffers may be read past M by TMA boxes: start from defined contents
-    RB_CUDA(cudaMemset(l.xn, 0, (size_t)(l.Mcap * d * pe)));
-    RB_CUDA(cudaMemset(l.ctx, 0, (size_t)(l.Mcap * inner * pe)));
-    RB_CUDA(cudaMemset(l.hbuf, 0, (size_t)(l.Mcap * dff * pe)));
-    RB_TRY(rb200_beam_create(cfg->device, lane_batch, cfg->max_beams, e->Lmodel, e->V, &l.beam));
-    RB_CUDA(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
-    if (li > 0) RB_CUDA(cudaStreamCreateWithFlags(&l.own_stream, cudaStreamNonBlocking));
-  }
-  RB_CUDA(cudaEventCreateWithFlags(&e->fork, cudaEventDisableTiming));
-  const int64_t Rall = (int64_t)cfg->max_batch * cfg->max_beams, BSall = (int64_t)cfg->max_batch * cfg->max_src_len;
-  RB_TRY(dev_alloc(e, (void**)&e->ids_dev, BSall * 8));
-  RB_TRY(dev_alloc(e, (void**)&e->mask_dev, BSall * 8));
-  RB_TRY(dev_alloc(e, (void**)&e->seq_dev, Rall * (e->Lmodel + 1) * 8));
-  RB_TRY(dev_alloc(e, (void**)&e->score_dev, Rall * 4));
-  RB_TRY(dev_alloc(e, (void**)&e->leaf_dev, Rall * 2 * 4));
   RB_TRY(dev_alloc(e, (void**)&e->overflow, 2 * 4));
   RB_CUDA(cudaMemset(e->overflow, 0, 8));
+  return alloc_workspace(e, cfg->max_batch, cfg->max_beams, cfg->max_src_len);
+}
+
+// Everything whose size depends on (max_batch, max_beams, max_src_len): activations, KV cache, beam state, host-call
+// staging. Kept apart from the packed weights so that rb200_engine_resize never touches those.
+static void free_workspace(rb200_engine* e) {
+  Lane& l = e->lanes[0];
+  void* lb[] = {l.x, l.x_full, l.xn, l.qkv, l.q2, l.ctx, l.hbuf, l.logits, l.cross_kv, l.enc_out, l.cache_k, l.cache_v,
+                l.ss[0], l.ss[1], e->ids_dev, e->mask_dev, e->seq_dev, e->score_dev, e->leaf_dev, e->enc_bias};
+  for (void* b : lb) cudaFree(b);
+  rb200_beam_free(l.beam);
+  l = Lane();
+  e->ids_dev = e->mask_dev = e->seq_dev = nullptr;
+  e->score_dev = nullptr; e->leaf_dev = nullptr; e->enc_bias = nullptr; e->enc_bias_S = 0;
+  e->ws_bytes -= e->ws_only_bytes;
+  e->ws_only_bytes = 0;
+}
+
+static int alloc_workspace(rb200_engine* e, int max_batch, int max_beams, int max_src_len) {
+  const int d = e->d, inner = e->inner, dff = e->dff;
+  const auto& cfg = e->cfg;
+  const int64_t before = e->ws_bytes;
+  const int64_t pe = (int64_t)e->planes * e->elem;
+  Lane& l = e->lanes[0];
+  l.Rcap = (int64_t)max_batch * max_beams;
+  l.BScap = (int64_t)max_batch * max_src_len;
+  // the forced tail runs up to min(Lmodel, RB_TAIL_MAX_L) positions of every beam row in one pass
+  const int tail_pos = e->Lmodel < RB_TAIL_MAX_L ? e->Lmodel : RB_TAIL_MAX_L;
+  l.Mcap = std::max(l.Rcap * tail_pos, l.BScap);
+  RB_TRY(dev_alloc(e, (void**)&l.x, l.Mcap * d * 4));
+  RB_TRY(dev_alloc(e, (void**)&l.x_full, l.Rcap * d * 4));
+  RB_TRY(dev_alloc(e, &l.xn, l.Mcap * d * pe));
+  RB_TRY(dev_alloc(e, (void**)&l.qkv, l.Mcap * 3 * inner * 4));
+  RB_TRY(dev_alloc(e, (void**)&l.q2, l.Mcap * inner * 4));
+  RB_TRY(dev_alloc(e, &l.ctx, l.Mcap * inner * pe));
+  RB_TRY(dev_alloc(e, &l.hbuf, l.Mcap * dff * pe));
+  RB_TRY(dev_alloc(e, (void**)&l.logits, l.Mcap * e->V * 4));
+  RB_TRY(dev_alloc(e, (void**)&l.cross_kv, l.BScap * cfg.num_decoder_layers * 2 * inner * 4));
+  RB_TRY(dev_alloc(e, (void**)&l.enc_out, l.BScap * d * 4));
+  const int64_t cache = (int64_t)cfg.num_decoder_layers * e->Lmodel * l.Rcap * inner * 4;
+  RB_TRY(dev_alloc(e, (void**)&l.cache_k, cache));
+  RB_TRY(dev_alloc(e, (void**)&l.cache_v, cache));
+  for (int b = 0; b < 2; ++b) RB_TRY(dev_alloc(e, (void**)&l.ss[b], l.Mcap * std::max(e->np, 1) * 4));
+  // planes of the activation buffers may be read past M by TMA boxes: start from defined contents
+  RB_CUDA(cudaMemset(l.xn, 0, (size_t)(l.Mcap * d * pe)));
+  RB_CUDA(cudaMemset(l.ctx, 0, (size_t)(l.Mcap * inner * pe)));
+  RB_CUDA(cudaMemset(l.hbuf, 0, (size_t)(l.Mcap * dff * pe)));
+  RB_TRY(rb200_beam_create(cfg.device, max_batch, max_beams, e->Lmodel, e->V, &l.beam));
+  RB_TRY(dev_alloc(e, (void**)&e->ids_dev, l.BScap * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->mask_dev, l.BScap * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->seq_dev, l.Rcap * (e->Lmodel + 1) * 8));
+  RB_TRY(dev_alloc(e, (void**)&e->score_dev, l.Rcap * 4));
+  RB_TRY(dev_alloc(e, (void**)&e->leaf_dev, l.Rcap * 2 * 4));
+  e->ws_batch = max_batch; e->ws_beams = max_beams; e->ws_src = max_src_len;
+  e->cfg.max_batch = max_batch; e->cfg.max_beams = max_beams; e->cfg.max_src_len = max_src_len;
+  e->ws_only_bytes = e->ws_bytes - before;
   return 0;
 }
 
@@ -373,18 +388,9 @@ int rb200_engine_free(rb200_engine* e) {
   fp(e->ckv);
   for (auto& p : e->out_tab) fp(p);
   for (auto p : e->in_tab) cudaFree(p);
-  void* bufs[] = {e->shared_emb, e->start_emb, e->enc_final_ln, e->dec_final_ln, e->dec_bias, e->enc_bias,
-                  e->ids_dev, e->mask_dev, e->seq_dev, e->score_dev, e->leaf_dev, e->overflow};
+  void* bufs[] = {e->shared_emb, e->start_emb, e->enc_final_ln, e->dec_final_ln, e->dec_bias, e->overflow};
   for (void* b : bufs) cudaFree(b);
-  for (Lane& l : e->lanes) {
-    void* lb[] = {l.x, l.xn, l.qkv, l.q2, l.ctx, l.hbuf, l.logits, l.cross_kv, l.enc_out, l.cache_k, l.cache_v,
-                  l.ss[0], l.ss[1]};
-    for (void* b : lb) cudaFree(b);
-    rb200_beam_free(l.beam);
-    if (l.done) cudaEventDestroy(l.done);
-    if (l.own_stream) cudaStreamDestroy(l.own_stream);
-  }
-  if (e->fork) cudaEventDestroy(e->fork);
+  free_workspace(e);
   cudaFree(e->in_tab_dev);
   if (e->flag_host) cudaFreeHost(e->flag_host);
   for (auto& st : e->stash) cudaFree(st.src);
@@ -558,6 +564,7 @@ int lane_encode(rb200_engine* e, Lane& l, const int64_t* ids, const int64_t* mas
     rb::CrossAttnArgs ca;
     ca.q = l.qkv; ca.q_ld = 3 * inner; ca.kv = l.qkv; ca.ld = 3 * inner; ca.k_off = inner; ca.v_off = 2 * inner;
     ca.mask = mask; ca.M = (int)rows; ca.H = e->H; ca.S = S; ca.rows_per_query = S; ca.rel_bias = e->enc_bias;
+    ca.rel_S = e->enc_bias_S;
     return rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s);
   };
   if (e->fold) {
@@ -611,25 +618,30 @@ int lane_encode(rb200_engine* e, Lane& l, const int64_t* ids, const int64_t* mas
 
 int lane_decode_step(rb200_engine* e, Lane& l, const rb200_beam* beam, int t, float* logits, cudaStream_t s) {
   const int rpq = (t == 0) ? 1 : l.nb;
-  const int64_t M = (int64_t)l.B * rpq;
+  const int64_t M = (int64_t)beam->n_active * rpq;          // rows of the queries still stepping, compact order
+  const int32_t* qlist = beam->compacted ? beam->qlist : nullptr;
   const int d = e->d, inner = e->inner, dff = e->dff;
   const float eps = e->cfg.layer_norm_eps;
+  if (M == 0) return 0;
   if (t == 0) {
     RB_TRY(rb::launch_broadcast_row(e->start_emb, l.x, M, d, s));
+  } else {
+    // the previous beam step left the inputs at original row ids: pull the stepping queries' rows together
+    RB_TRY(rb::launch_gather_rows(beam, l.x_full, l.x, d, s));
   }
   const int64_t layer_cache = (int64_t)e->Lmodel * l.Rcap * inner;
   auto self_attn = [&](size_t i) {
     rb::SelfAttnArgs sa;
     sa.qkv = l.qkv; sa.cache_k = l.cache_k + i * layer_cache; sa.cache_v = l.cache_v + i * layer_cache;
     sa.anc = beam->anc[beam->cur]; sa.bias = e->dec_bias; sa.row_cap = l.Rcap;
-    sa.M = (int)M; sa.H = e->H; sa.L = e->Lmodel; sa.t = t; sa.rpq = rpq; sa.nb = l.nb;
+    sa.M = (int)M; sa.H = e->H; sa.L = e->Lmodel; sa.t = t; sa.rpq = rpq; sa.nb = l.nb; sa.qlist = qlist;
     return rb::launch_self_attn_decode(sa, e->act(l, l.ctx, inner), s);
   };
   auto cross_attn = [&](size_t i) {
     rb::CrossAttnArgs ca;
     ca.q = l.q2; ca.kv = l.cross_kv + (int64_t)i * l.BScap * 2 * inner; ca.ld = 2 * inner; ca.k_off = 0;
     ca.v_off = inner; ca.mask = l.cur_mask; ca.M = (int)M; ca.H = e->H; ca.S = l.S;
-    ca.rows_per_query = rpq;
+    ca.rows_per_query = rpq; ca.qmap = qlist;
     return rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s);
   };
   if (e->fold) {
@@ -682,17 +694,22 @@ int lane_decode_step(rb200_engine* e, Lane& l, const rb200_beam* beam, int t, fl
   return 0;
 }
 
-// Forced tail: positions t .. t+T-1 of every beam row of the lane in one teacher-forced pass (rows position-major:
-// row = j * R + r). Same kernels and per-row arithmetic as T decoder steps; what changes is that the GEMMs see
-// T*R rows at once, a lineage's K/V are read once for all T queries, and ~130 launches replace ~130*T.
-int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, int t, int T, int apply_log_softmax, cudaStream_t s) {
+// Forced tail: the remaining positions of every frozen query's beams in ONE teacher-forced pass (rows position-major
+// and ragged, see rb::TailLayout). Same kernels and per-row arithmetic as the decoder steps they replace; what changes
+// is that the GEMMs see all (row, position) pairs at once, a lineage's K/V are read once for all of its positions, and
+// ~130 launches replace ~130 per step. With trie == nullptr the tokens come from the beam state's forced history
+// (rb200_engine_forward: teacher forcing from position 0, no cached prefix).
+int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, const rb::TailLayout& lay, float* hidden_out,
+              cudaStream_t s) {
   rb200_beam* beam = l.beam;
-  const int R = l.B * l.nb;
-  const int64_t M = (int64_t)T * R;
+  const int nfz_rows = beam->n_frozen * beam->nb;
+  const int64_t M = lay.off[lay.P];
   const int d = e->d, inner = e->inner, dff = e->dff;
   const float eps = e->cfg.layer_norm_eps;
-  RB_REQUIRE(M <= l.Mcap, "forced tail of %lld rows exceeds the lane capacity %lld", (long long)M, (long long)l.Mcap);
-  RB_TRY(rb::launch_tail_prepare(beam, trie, T, e->in_tab_dev, l.x, d, s));
+  if (M == 0) return 0;
+  RB_REQUIRE(M <= l.Mcap, "forced tail of %lld rows exceeds the workspace capacity %lld", (long long)M, (long long)l.Mcap);
+  RB_TRY(rb::launch_tail_prepare(beam, trie, lay, e->in_tab_dev, e->start_emb, l.x, d, s));
+  const int32_t* qstart = trie ? beam->qstate : nullptr;
   const int64_t layer_cache = (int64_t)e->Lmodel * l.Rcap * inner;
   for (size_t i = 0; i < e->dec.size(); ++i) {
     Layer& w = e->dec[i];
@@ -700,16 +717,17 @@ int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, int t, int T, in
     RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
     rb::TailAttnArgs ta;
     ta.qkv = l.qkv; ta.cache_k = l.cache_k + i * layer_cache; ta.cache_v = l.cache_v + i * layer_cache;
-    ta.anc = beam->anc[beam->cur]; ta.bias = e->dec_bias; ta.row_cap = l.Rcap;
-    ta.R = R; ta.H = e->H; ta.L = e->Lmodel; ta.t = t; ta.T = T;
+    ta.anc = beam->fz_anc; ta.bias = e->dec_bias; ta.row_cap = l.Rcap;
+    ta.R = nfz_rows; ta.H = e->H; ta.L = e->Lmodel; ta.nb = beam->nb;
+    ta.fz_list = beam->fz_list; ta.qstart = qstart; ta.lay = lay;
     RB_TRY(rb::launch_self_attn_tail(ta, e->act(l, l.ctx, inner), s));
     RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
     RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
     rb::CrossAttnArgs ca;
     ca.q = l.q2; ca.kv = l.cross_kv + (int64_t)i * l.BScap * 2 * inner; ca.ld = 2 * inner; ca.k_off = 0;
-    ca.v_off = inner; ca.mask = l.cur_mask; ca.M = R; ca.H = e->H; ca.S = l.S; ca.rows_per_query = l.nb;
-    ca.nblocks = T; ca.block_rows = R;
+    ca.v_off = inner; ca.mask = l.cur_mask; ca.M = nfz_rows; ca.H = e->H; ca.S = l.S; ca.rows_per_query = beam->nb;
+    ca.qmap = beam->fz_list; ca.ragged = 1; ca.qstart = qstart; ca.lay = lay;
     RB_TRY(rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s));
     RB_TRY(gemm(e, l, l.ctx, inner, w.co, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln2, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
@@ -718,11 +736,14 @@ int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, int t, int T, in
   }
   const float scale = e->cfg.scaleup_output_hidden ? 1.0f / sqrtf((float)d) : 1.0f;
   RB_TRY(rb::launch_rmsnorm(l.x, e->dec_final_ln, e->act(l, l.xn, d), M, d, eps, scale, s));
+  if (hidden_out) RB_TRY(rb::launch_rmsnorm_f32(l.x, e->dec_final_ln, hidden_out, M, d, eps, s, scale));
   // LM head: the output table differs per position -> one GEMM per position block
-  for (int j = 0; j < T; ++j)
-    RB_TRY(gemm(e, l, static_cast<const char*>(l.xn) + (int64_t)j * R * d * e->elem, d, e->out_tab[t + j],
-                l.logits + (int64_t)j * R * e->V, e->V, ActOut{}, R, rb::EPI_STORE, s));
-  RB_TRY(rb::launch_tail_finish(beam, trie, T, l.logits, apply_log_softmax, s));
+  for (int p = 0; p < lay.P; ++p) {
+    const int64_t n_p = lay.off[p + 1] - lay.off[p];
+    if (n_p == 0) continue;
+    RB_TRY(gemm(e, l, static_cast<const char*>(l.xn) + (int64_t)lay.off[p] * d * e->elem, d, e->out_tab[p],
+                l.logits + (int64_t)lay.off[p] * e->V, e->V, ActOut{}, n_p, rb::EPI_STORE, s));
+  }
   return 0;
 }
 
@@ -771,6 +792,35 @@ int64_t rb200_engine_last_launch_count(const rb200_engine* e) { return e ? e->la
 
 int rb200_engine_last_tail_step(const rb200_engine* e) { return e ? e->last_tail_from : -1; }
 
+int rb200_engine_next_input(const rb200_engine* e, float** next_x) {
+  RB_REQUIRE(e && next_x, "null argument");
+  *next_x = e->lanes[0].x_full;
+  return 0;
+}
+
+int rb200_engine_resize(rb200_engine* e, int max_batch, int max_beams, int max_src_len) {
+  RB_REQUIRE(e, "null argument");
+  RB_REQUIRE(max_batch >= 1 && max_beams >= 1 && max_src_len >= 1, "max_batch, max_beams, max_src_len must be >= 1");
+  if (max_batch == e->ws_batch && max_beams == e->ws_beams && max_src_len == e->ws_src) return 0;
+  RB_CUDA(cudaSetDevice(e->cfg.device));
+  RB_CUDA(cudaDeviceSynchronize());
+  free_workspace(e);
+  const int st = alloc_workspace(e, max_batch, max_beams, max_src_len);
+  if (st != 0) {                      // keep the handle usable: nothing is allocated, the next resize may succeed
+    free_workspace(e);
+    e->ws_batch = e->ws_beams = e->ws_src = 0;
+    e->cfg.max_batch = e->cfg.max_beams = e->cfg.max_src_len = 0;
+  }
+  return st;
+}
+
+int rb200_engine_last_freeze_histogram(const rb200_engine* e, int32_t* frozen_at, int n, int64_t* tail_rows) {
+  RB_REQUIRE(e && frozen_at && n >= 1, "null argument");
+  for (int t = 0; t < n; ++t) frozen_at[t] = t <= RB_TAIL_MAX_L ? e->frozen_at[t] : 0;
+  if (tail_rows) *tail_rows = e->last_tail_rows;
+  return 0;
+}
+
 int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* ids, const int64_t* mask, int batch,
                         int S, int num_beams, int max_new_tokens, int num_return, int apply_log_softmax,
                         int64_t* sequences, float* scores, int32_t* leaf, void* stream) {
@@ -778,8 +828,8 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
   if (!e->finalized) return rb::fail(RB200_ERR_STATE, "weights not finalized: call rb200_engine_finalize_weights");
   RB_REQUIRE(batch >= 1 && batch <= e->cfg.max_batch, "batch %d outside [1, %d]", batch, e->cfg.max_batch);
   RB_REQUIRE(S >= 1 && S <= e->cfg.max_src_len, "source length %d outside [1, %d]", S, e->cfg.max_src_len);
-  RB_REQUIRE(num_beams == e->cfg.max_beams, "the engine was created for num_beams=%d, got %d", e->cfg.max_beams,
-             num_beams);
+  RB_REQUIRE(num_beams >= 1 && num_beams <= e->cfg.max_beams, "num_beams %d outside [1, %d]", num_beams,
+             e->cfg.max_beams);
   RB_REQUIRE(max_new_tokens >= 1 && max_new_tokens <= e->Lmodel && max_new_tokens <= trie->L,
              "max_new_tokens=%d outside [1, min(model %d, trie %d)]", max_new_tokens, e->Lmodel, trie->L);
   RB_REQUIRE(num_return >= 1 && num_return <= num_beams,
@@ -790,55 +840,55 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
   const int64_t launches0 = rb::launch_count();
   RB_CUDA(cudaMemsetAsync(e->overflow, 0, 4, s0));
   RB_TRY(build_bias_tables(e, S, s0));
-  // Split the batch over the two lanes when it is large enough to keep both busy (the profiling pass keeps one
-  // lane so that the per-GEMM event times are not inflated by the other lane's kernels).
-  const bool split = e->num_lanes == 2 && !e->profiling && batch >= 16 && batch / 2 <= e->cfg.max_batch / 2;
-  const int nl = split ? 2 : 1;
-  int q0[3] = {0, split ? (batch + 1) / 2 : batch, batch};
-  if (split && batch - q0[1] > e->cfg.max_batch / 2) q0[1] = batch - e->cfg.max_batch / 2;
-  cudaStream_t ls[2] = {s0, e->lanes[1].own_stream};
-  if (split) {
-    RB_CUDA(cudaEventRecord(e->fork, s0));
-    RB_CUDA(cudaStreamWaitEvent(ls[1], e->fork, 0));
-  }
-  for (int li = 0; li < nl; ++li) {
-    Lane& l = e->lanes[li];
-    const int nq = q0[li + 1] - q0[li];
-    RB_TRY(lane_encode(e, l, ids + (int64_t)q0[li] * S, mask + (int64_t)q0[li] * S, nq, S, num_beams, ls[li]));
-    RB_TRY(rb200_beam_reset(l.beam, trie, nq, ls[li]));
-  }
-  // The forced tail needs a host decision: after each of the first steps the count of beams that are not yet on a
-  // single trie leaf comes back (4 bytes; the launch queue is ~a step ahead of the GPU, so the sync costs little).
-  const bool try_tail = e->tail && !e->fold && nl == 1 && max_new_tokens <= 32;
+  Lane& l = e->lanes[0];
+  rb200_beam* beam = l.beam;
+  RB_TRY(lane_encode(e, l, ids, mask, batch, S, num_beams, s0));
+  RB_TRY(rb200_beam_reset_beams(beam, trie, batch, num_beams, s0));
+  // Forced tail, per query: after every beam step the queries whose beams all sit on a single trie leaf are frozen
+  // (their remaining tokens are determined by the trie) and leave the step loop; the loop goes on with the others as
+  // a compacted batch. The host reads two counters back per step (stepping / frozen) to size the next launches.
+  const int P = max_new_tokens;
+  const bool try_tail = e->tail && !e->fold && P <= RB_TAIL_MAX_L;
   e->last_tail_from = -1;
-  for (int t = 0; t < max_new_tokens; ++t) {
-    const bool more = t + 1 < max_new_tokens;
-    for (int li = 0; li < nl; ++li) {
-      Lane& l = e->lanes[li];
-      RB_TRY(lane_decode_step(e, l, l.beam, t, l.logits, ls[li]));
-      RB_TRY(rb200_beam_step(l.beam, trie, l.logits, t == 0 ? 1 : num_beams, apply_log_softmax,
-                             more ? e->in_tab[t] : nullptr, more ? l.x : nullptr, e->d, ls[li]));
-    }
-    const int left = max_new_tokens - (t + 1);
-    if (try_tail && left >= 2 && t < 12) {
-      RB_CUDA(cudaMemcpyAsync(e->flag_host, e->lanes[0].beam->not_forced, sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
+  e->last_tail_rows = 0;
+  for (int t = 0; t <= RB_TAIL_MAX_L; ++t) e->frozen_at[t] = 0;
+  for (int t = 0; t < P && beam->n_active > 0; ++t) {
+    const bool more = t + 1 < P;
+    RB_TRY(lane_decode_step(e, l, beam, t, l.logits, s0));
+    const int allow = try_tail && more;
+    RB_TRY(rb::beam_step(beam, trie, l.logits, t == 0 ? 1 : num_beams, apply_log_softmax,
+                         more ? e->in_tab[t] : nullptr, more ? l.x_full : nullptr, e->d, allow, s0));
+    if (allow) {
+      RB_TRY(rb::beam_compact(beam, s0));
+      RB_CUDA(cudaMemcpyAsync(e->flag_host, beam->counts, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, s0));
       RB_CUDA(cudaStreamSynchronize(s0));
-      if (*e->flag_host == 0) {
-        RB_TRY(lane_tail(e, e->lanes[0], trie, t + 1, left, apply_log_softmax, s0));
-        e->last_tail_from = t + 1;
-        break;
+      const int n_act = e->flag_host[0], n_fz = e->flag_host[1];
+      e->frozen_at[t + 1] = n_fz - beam->n_frozen;
+      if (n_fz > beam->n_frozen && e->last_tail_from < 0) e->last_tail_from = t + 1;
+      beam->n_active = n_act;
+      beam->n_frozen = n_fz;
+      beam->compacted = n_fz > 0;
+    }
+  }
+  if (beam->n_frozen > 0) {
+    rb::TailLayout lay;
+    lay.P = P;
+    int64_t off = 0, rows = 0;
+    for (int p = 0; p <= RB_TAIL_MAX_L; ++p) {
+      lay.off[p] = (int)off;
+      if (p < P) {
+        rows += (int64_t)e->frozen_at[p] * num_beams;     // block p: the beams of the queries frozen at or before p
+        off += rows;
       }
     }
+    RB_REQUIRE(off <= 0x7fffffff, "forced tail of %lld rows", (long long)off);
+    e->last_tail_rows = off;
+    RB_TRY(lane_tail(e, l, trie, lay, nullptr, s0));
+    RB_TRY(rb::launch_tail_finish(beam, trie, lay, l.logits, apply_log_softmax, s0));
   }
-  for (int li = 0; li < nl; ++li) {
-    const int64_t o = (int64_t)q0[li] * num_return;
-    RB_TRY(rb200_beam_finalize(e->lanes[li].beam, trie, num_return, 1.0, sequences + o * (max_new_tokens + 1),
-                               scores + o, leaf ? leaf + o * 2 : nullptr, ls[li]));
-  }
-  if (split) {
-    RB_CUDA(cudaEventRecord(e->lanes[1].done, ls[1]));
-    RB_CUDA(cudaStreamWaitEvent(s0, e->lanes[1].done, 0));
-  }
+  beam->step = P;
+  beam->n_active = batch; beam->n_frozen = 0; beam->compacted = false;   // the final state is whole in the current half
+  RB_TRY(rb200_beam_finalize(beam, trie, num_return, 1.0, sequences, scores, leaf, s0));
   if (rb::prec_is_fp16(e->mode)) {
     const int n = batch * num_return;
     poison_on_overflow_kernel<<<rb::ceil_div(n, 256), 256, 0, s0>>>(scores, n, e->overflow);
@@ -868,6 +918,45 @@ int rb200_engine_search_host(rb200_engine* e, const rb200_trie* trie, const int6
   RB_CUDA(cudaMemcpyAsync(scores_host, e->score_dev, n * 4, cudaMemcpyDeviceToHost, s));
   if (leaf_host) RB_CUDA(cudaMemcpyAsync(leaf_host, e->leaf_dev, n * 2 * 4, cudaMemcpyDeviceToHost, s));
   RB_CUDA(cudaStreamSynchronize(s));
+  return 0;
+}
+
+// Teacher-forced decoder pass over given DocID tokens (no beam search): what the reference's model forward computes
+// when it is handed decoder_input_ids (t5_generative_retriever.py:295-450), and what rerank_forward sums (:794-798).
+int rb200_engine_forward(rb200_engine* e, const int64_t* ids, const int64_t* mask, int batch, int S, int rows_per_query,
+                         const int32_t* tokens, int T, float* logits_out, float* hidden_out, float* scores_out,
+                         void* stream) {
+  RB_REQUIRE(e && ids && mask && tokens, "null argument");
+  if (!e->finalized) return rb::fail(RB200_ERR_STATE, "weights not finalized: call rb200_engine_finalize_weights");
+  RB_REQUIRE(batch >= 1 && batch <= e->cfg.max_batch, "batch %d outside [1, %d]", batch, e->cfg.max_batch);
+  RB_REQUIRE(S >= 1 && S <= e->cfg.max_src_len, "source length %d outside [1, %d]", S, e->cfg.max_src_len);
+  RB_REQUIRE(rows_per_query >= 1 && rows_per_query <= e->cfg.max_beams, "rows_per_query %d outside [1, %d]",
+             rows_per_query, e->cfg.max_beams);
+  RB_REQUIRE(T >= 1 && T <= e->Lmodel && T <= RB_TAIL_MAX_L, "T=%d outside [1, min(model %d, %d)]", T, e->Lmodel,
+             RB_TAIL_MAX_L);
+  cudaStream_t s0 = (cudaStream_t)stream;
+  RB_CUDA(cudaSetDevice(e->cfg.device));
+  const int64_t launches0 = rb::launch_count();
+  RB_CUDA(cudaMemsetAsync(e->overflow, 0, 4, s0));
+  RB_TRY(build_bias_tables(e, S, s0));
+  Lane& l = e->lanes[0];
+  RB_TRY(lane_encode(e, l, ids, mask, batch, S, rows_per_query, s0));
+  RB_TRY(rb::beam_force_tokens(l.beam, batch, rows_per_query, T, tokens, s0));
+  const int R = batch * rows_per_query;
+  rb::TailLayout lay;
+  lay.P = T;
+  for (int p = 0; p <= RB_TAIL_MAX_L; ++p) lay.off[p] = (p < T ? p : T) * R;
+  RB_TRY(lane_tail(e, l, nullptr, lay, hidden_out, s0));
+  const size_t nlog = (size_t)T * R * e->V;
+  if (scores_out) RB_TRY(rb::launch_forced_scores(l.beam, lay, l.logits, scores_out, s0));
+  if (logits_out) RB_CUDA(cudaMemcpyAsync(logits_out, l.logits, nlog * 4, cudaMemcpyDeviceToDevice, s0));
+  if (rb::prec_is_fp16(e->mode)) {    // an activation left the fp16 range: unmistakably invalid results
+    if (scores_out) poison_on_overflow_kernel<<<rb::ceil_div(R, 256), 256, 0, s0>>>(scores_out, R, e->overflow);
+    if (logits_out) poison_on_overflow_kernel<<<1, 32, 0, s0>>>(logits_out, 1, e->overflow);
+    RB_CUDA(cudaGetLastError());
+  }
+  l.beam->n_active = 0; l.beam->n_frozen = 0; l.beam->batch = 0;   // the beam state holds no search
+  e->launches = rb::launch_count() - launches0;
   return 0;
 }
 

@@ -209,8 +209,9 @@ int launch_rmsnorm(const float* x, const float* w, ActOut out, int64_t rows, int
   return launch_rmsnorm_any<false>(x, w, out, nullptr, rows, d, eps, scale, s);
 }
 
-int launch_rmsnorm_f32(const float* x, const float* w, float* out, int64_t rows, int d, float eps, cudaStream_t s) {
-  return launch_rmsnorm_any<true>(x, w, ActOut{nullptr, 0, 0}, out, rows, d, eps, 1.0f, s);
+int launch_rmsnorm_f32(const float* x, const float* w, float* out, int64_t rows, int d, float eps, cudaStream_t s,
+                       float scale) {
+  return launch_rmsnorm_any<true>(x, w, ActOut{nullptr, 0, 0}, out, rows, d, eps, scale, s);
 }
 
 // attn_warp.cu: the attention kernels (one warp per (row, head)); the encoder reuses the cross-attention kernel

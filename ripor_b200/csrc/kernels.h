@@ -1,6 +1,7 @@
 // Launchers of the engine's non-tensor-core kernels and of the two GEMM back ends.
 #pragma once
 #include "act.cuh"
+#include "beam.h"
 #include "rb_common.h"
 
 namespace rb {
@@ -57,7 +58,8 @@ int launch_rmsnorm(const float* x, const float* w, ActOut out, int64_t rows, int
 int launch_norm_init(const float* x, ActOut out, float* ss0, float* ss1, int np, int64_t rows, int d, float eps,
                      cudaStream_t s);
 // same, fp32 output (encoder last_hidden_state)
-int launch_rmsnorm_f32(const float* x, const float* w, float* out, int64_t rows, int d, float eps, cudaStream_t s);
+int launch_rmsnorm_f32(const float* x, const float* w, float* out, int64_t rows, int d, float eps, cudaStream_t s,
+                       float scale = 1.0f);
 
 struct SelfAttnArgs {
   const float* qkv;       // [M, 3*inner] (q | k | v) of the current position
@@ -67,6 +69,9 @@ struct SelfAttnArgs {
   const float* bias;      // [H, L] relative position bias by distance (t - p)
   int64_t row_cap;
   int M, H, L, t, rpq, nb;
+  // compact rows (some queries have left the step loop): row m belongs to query qlist[m / nb]; the cache slots and
+  // the ancestry table keep the ORIGINAL row ids. nullptr = identity.
+  const int32_t* qlist = nullptr;
 };
 int launch_self_attn_decode(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s);
 
@@ -83,20 +88,33 @@ struct CrossAttnArgs {
   // encoder self-attention through the same kernel: the "beams" are the S query rows of the sequence and every score
   // gets the relative position bias rel_bias[h][(key - query) + S - 1]
   const float* rel_bias = nullptr;
+  int rel_S = 0;            // the table was built for sequences of up to rel_S positions: [H, 2*rel_S-1]
+  // compact query index -> query whose encoder K/V and mask to use (step loop: the stepping list; forced tail: the
+  // freeze-order list). nullptr = identity.
+  const int32_t* qmap = nullptr;
+  // ragged forced tail: query slot fq runs positions qstart[qmap[fq]] (0 if qstart is null) .. lay.P-1 and its rows
+  // are lay.off[p] + fq * rows_per_query + beam (nblocks / block_rows are then ignored; M = slots * rows_per_query)
+  int ragged = 0;
+  const int32_t* qstart = nullptr;
+  TailLayout lay;
 };
 int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s);
 
-// Self-attention of the forced tail: T consecutive positions t..t+T-1 of every beam row in one launch. Rows are
-// position-major (row = j * R + r); positions < t come from the KV cache through the ancestry table, positions >= t
-// from the rows of this pass. Requires t + T <= 32.
+// Self-attention of the forced tail: every frozen row r' (freeze order) runs its remaining positions t0..P-1 in one
+// task. Rows are position-major and ragged (row = lay.off[p] + r'); positions < t0 come from the KV cache through the
+// frozen ancestry table (indexed by the ORIGINAL row id), positions >= t0 from the rows of this pass. P <= 32.
 struct TailAttnArgs {
-  const float* qkv;       // [T*R, 3*inner]
+  const float* qkv;       // [rows of the pass, 3*inner]
   const float* cache_k;   // this layer's cache [L, row_cap, inner]
   const float* cache_v;
-  const int32_t* anc;     // [R, L]
+  const int32_t* anc;     // [R, L] frozen ancestry
   const float* bias;      // [H, L]
   int64_t row_cap;
-  int R, H, L, t, T;
+  int R;                  // frozen rows = frozen queries * nb
+  int H, L, nb;
+  const int32_t* fz_list; // frozen slot -> query
+  const int32_t* qstart;  // per query: first position of the pass (nullptr: 0 for all, no cached prefix)
+  TailLayout lay;
 };
 int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s);
 

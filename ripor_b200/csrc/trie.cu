@@ -5,7 +5,9 @@
 #include <cstdio>
 #include <cstring>
 #include <numeric>
+#include <string>
 #include <thread>
+#include <unistd.h>
 
 #include "rb_common.h"
 #include "trie.h"
@@ -179,7 +181,37 @@ __global__ void trie_mask_kernel(TrieView tv, const int64_t* __restrict__ ids, i
   for (int v = lane; v < tv.V; v += 32) mask[row * tv.V + v] = (bm[v >> 5] >> (v & 31)) & 1u ? 1.0 : 0.0;
 }
 
-static const char kMagic[8] = {'R', 'B', '2', 'T', 'R', 'I', 'E', '1'};
+// One warp per output row: the input rows (documents) under the row's leaf range [lo, hi), ascending = the order of
+// docid_to_smtid.json (evaluate.py:439-446 appends docids in json iteration order). leaf_docs is grouped by leaf with
+// input order inside a leaf, so a single leaf is copied as is; a range of several leaves (prefix search) is rank-sorted.
+__global__ void leaf_expand_kernel(const int32_t* __restrict__ leaf_ptr, const int32_t* __restrict__ leaf_docs,
+                                   const int32_t* __restrict__ ranges, int64_t n, int k, int64_t* __restrict__ docs,
+                                   int32_t* __restrict__ counts) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  const int lo = ranges[row * 2], hi = ranges[row * 2 + 1];
+  const int beg = hi > lo ? leaf_ptr[lo] : 0, end = hi > lo ? leaf_ptr[hi] : 0;
+  const int cnt = end - beg;
+  if (lane == 0) counts[row] = cnt;
+  int64_t* out = docs + row * k;
+  if (cnt > k) {                                   // does not fit: the caller expands this row on the host
+    for (int e = lane; e < k; e += 32) out[e] = -1;
+    return;
+  }
+  for (int e = lane; e < k; e += 32) {
+    if (e >= cnt) { out[e] = -1; continue; }
+    const int v = leaf_docs[beg + e];
+    int rank = e;
+    if (hi - lo > 1) {
+      rank = 0;
+      for (int j = 0; j < cnt; ++j) rank += leaf_docs[beg + j] < v;      // row ids are distinct
+    }
+    out[rank] = v;
+  }
+}
+
+static const char kMagic[8] = {'R', 'B', '2', 'T', 'R', 'I', 'E', '2'};
 
 template <typename T>
 static bool wr(FILE* f, const std::vector<T>& v) {
@@ -219,6 +251,7 @@ int rb200_trie_free(rb200_trie* tr) {
   if (tr->device >= 0) {
     cudaFree(tr->d_codes); cudaFree(tr->d_node_bitmap); cudaFree(tr->d_node_child_ptr);
     cudaFree(tr->d_child_lo); cudaFree(tr->d_child_node);
+    cudaFree(tr->d_leaf_ptr); cudaFree(tr->d_leaf_docs);
   }
   delete tr;
   return 0;
@@ -240,30 +273,39 @@ int rb200_trie_level_counts(const rb200_trie* tr, int64_t* counts) {
   return 0;
 }
 
-int rb200_trie_save(const rb200_trie* tr, const char* path) {
+int rb200_trie_save_tagged(const rb200_trie* tr, const char* path, uint64_t source_tag) {
   RB_REQUIRE(tr && path, "null argument");
-  FILE* f = fopen(path, "wb");
-  if (!f) return rb::fail(RB200_ERR_IO, "cannot open %s for writing", path);
-  int64_t hdr[6] = {tr->L, tr->V, tr->code_bytes, tr->n_docs, tr->U, tr->root_node};
-  bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(hdr, 8, 6, f) == 6 && wr(f, tr->codes) &&
+  // written next to the target and renamed into place: a reader never sees a half-written cache
+  const std::string tmp = std::string(path) + ".tmp." + std::to_string((long long)getpid());
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) return rb::fail(RB200_ERR_IO, "cannot open %s for writing", tmp.c_str());
+  int64_t hdr[7] = {tr->L, tr->V, tr->code_bytes, tr->n_docs, tr->U, tr->root_node, (int64_t)source_tag};
+  bool ok = fwrite(kMagic, 8, 1, f) == 1 && fwrite(hdr, 8, 7, f) == 7 && wr(f, tr->codes) &&
             wr(f, tr->node_bitmap) && wr(f, tr->node_child_ptr) && wr(f, tr->child_lo) && wr(f, tr->child_node) &&
             wr(f, tr->leaf_ptr) && wr(f, tr->leaf_docs) && wr(f, tr->level_counts);
   ok = (fclose(f) == 0) && ok;
-  if (!ok) return rb::fail(RB200_ERR_IO, "short write to %s", path);
+  if (ok) ok = rename(tmp.c_str(), path) == 0;
+  if (!ok) {
+    remove(tmp.c_str());
+    return rb::fail(RB200_ERR_IO, "short write to %s", path);
+  }
   return 0;
 }
 
-int rb200_trie_load(const char* path, rb200_trie** out) {
+int rb200_trie_save(const rb200_trie* tr, const char* path) { return rb200_trie_save_tagged(tr, path, 0); }
+
+int rb200_trie_load_tagged(const char* path, uint64_t* source_tag, rb200_trie** out) {
   RB_REQUIRE(path && out, "null argument");
   FILE* f = fopen(path, "rb");
   if (!f) return rb::fail(RB200_ERR_IO, "cannot open %s", path);
   char magic[8];
-  int64_t hdr[6];
+  int64_t hdr[7];
   rb200_trie* tr = new rb200_trie();
-  bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0 && fread(hdr, 8, 6, f) == 6;
+  bool ok = fread(magic, 8, 1, f) == 1 && memcmp(magic, kMagic, 8) == 0 && fread(hdr, 8, 7, f) == 7;
   if (ok) {
     tr->L = (int)hdr[0]; tr->V = (int)hdr[1]; tr->code_bytes = (int)hdr[2]; tr->n_docs = hdr[3]; tr->U = hdr[4];
     tr->root_node = (int)hdr[5];
+    if (source_tag) *source_tag = (uint64_t)hdr[6];
     tr->words = (tr->V + 31) / 32;
     ok = rd(f, tr->codes) && rd(f, tr->node_bitmap) && rd(f, tr->node_child_ptr) && rd(f, tr->child_lo) &&
          rd(f, tr->child_node) && rd(f, tr->leaf_ptr) && rd(f, tr->leaf_docs) && rd(f, tr->level_counts);
@@ -275,6 +317,8 @@ int rb200_trie_load(const char* path, rb200_trie** out) {
   *out = tr;
   return 0;
 }
+
+int rb200_trie_load(const char* path, rb200_trie** out) { return rb200_trie_load_tagged(path, nullptr, out); }
 
 int rb200_trie_mask_host(const rb200_trie* tr, const int64_t* ids, int64_t R, int T, double* mask) {
   RB_REQUIRE(tr && ids && mask, "null argument");
@@ -326,6 +370,32 @@ int rb200_trie_upload(rb200_trie* tr, int device) {
   RB_CUDA(up((void**)&tr->d_child_node, tr->child_node.data(), 4 * tr->child_node.size()));
   tr->device = device;
   RB_CUDA(cudaSetDevice(prev));
+  return 0;
+}
+
+int rb200_trie_leaf_expand(rb200_trie* tr, const int32_t* leaf_ranges, int64_t n, int k, int64_t* docs, int32_t* counts,
+                           void* stream) {
+  RB_REQUIRE(tr && leaf_ranges && docs && counts, "null argument");
+  RB_REQUIRE(k >= 1 && k <= 4096, "max_docs_per_row=%d outside [1, 4096]", k);
+  if (tr->device < 0) return rb::fail(RB200_ERR_STATE, "trie not uploaded: call rb200_trie_upload first");
+  if (n == 0) return 0;
+  if (tr->d_leaf_ptr == nullptr) {                 // first use: the leaf -> documents CSR goes to HBM as int32
+    RB_REQUIRE(tr->n_docs < 0x7fffffff, "too many documents for the device leaf table");
+    std::vector<int32_t> p32(tr->leaf_ptr.begin(), tr->leaf_ptr.end()), d32(tr->leaf_docs.begin(), tr->leaf_docs.end());
+    int prev = 0;
+    RB_CUDA(cudaGetDevice(&prev));
+    RB_CUDA(cudaSetDevice(tr->device));
+    RB_CUDA(cudaMalloc((void**)&tr->d_leaf_ptr, p32.size() * 4));
+    RB_CUDA(cudaMalloc((void**)&tr->d_leaf_docs, d32.size() * 4 + 4));
+    RB_CUDA(cudaMemcpy(tr->d_leaf_ptr, p32.data(), p32.size() * 4, cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(tr->d_leaf_docs, d32.data(), d32.size() * 4, cudaMemcpyHostToDevice));
+    RB_CUDA(cudaSetDevice(prev));
+  }
+  const int warps = 4;
+  leaf_expand_kernel<<<rb::ceil_div(n, warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      tr->d_leaf_ptr, tr->d_leaf_docs, leaf_ranges, n, k, docs, counts);
+  RB_CUDA(cudaGetLastError());
+  rb::launch_count()++;
   return 0;
 }
 

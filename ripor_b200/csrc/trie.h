@@ -113,6 +113,8 @@ struct rb200_trie {
   int32_t* d_node_child_ptr = nullptr;
   int32_t* d_child_lo = nullptr;
   int32_t* d_child_node = nullptr;
+  int32_t* d_leaf_ptr = nullptr;       // [U+1] (rb200_trie_leaf_expand; uploaded on first use)
+  int32_t* d_leaf_docs = nullptr;      // [n_docs]
 
   rb::TrieView host_view() const;
   rb::TrieView device_view() const;

@@ -18,7 +18,8 @@ from __future__ import annotations
 import argparse
 import json
 import os
-import pickle
+import queue
+import threading
 from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
@@ -26,7 +27,8 @@ import torch
 
 from .generation import PrefixConstrainLogitProcessorFastSparse, generate_for_constrained_prefix_beam_search
 from .modeling import T5SeqAQEncoder
-from .trie import DocidTrie
+from . import _lib
+from .trie import DocidTrie, source_tag
 from .utils import convert_ptsmtids_to_strsmtid, get_dataset_name
 
 QUERY_PREFIX = "query: "          # reference dataset/dataset.py:15
@@ -119,9 +121,79 @@ class CollectionDataWithDocIDLoader:
                    "id": torch.tensor([int(i) for i in id_], dtype=torch.long)}
 
 
+class PrefetchLoader:
+    """Double-buffered query feed: a worker thread tokenises and pins the next batches while the GPU searches the
+    current one (the reference gets the same overlap from DataLoader(num_workers=1, pin_memory=True),
+    dataloader.py:19, evaluate.py:467). ``device`` set: the H2D copies are issued from the consumer side with
+    non_blocking=True out of the pinned buffers."""
+
+    def __init__(self, loader, depth: int = 2, device=None):
+        self.loader, self.depth, self.device = loader, max(1, depth), device
+
+    def __len__(self):
+        return len(self.loader)
+
+    def __iter__(self):
+        q: "queue.Queue" = queue.Queue(maxsize=self.depth)
+        stop = threading.Event()
+
+        def work():
+            try:
+                for batch in self.loader:
+                    while not stop.is_set():
+                        try:
+                            q.put(batch, timeout=0.1)
+                            break
+                        except queue.Full:
+                            continue
+                    if stop.is_set():
+                        return
+                q.put(None)
+            except BaseException as exc:          # surfaced on the consumer side
+                q.put(exc)
+
+        th = threading.Thread(target=work, daemon=True)
+        th.start()
+        try:
+            while True:
+                item = q.get()
+                if item is None:
+                    break
+                if isinstance(item, BaseException):
+                    raise item
+                if self.device is not None:
+                    item = {k: (v.to(self.device, non_blocking=True) if k != "id" else v) for k, v in item.items()}
+                yield item
+        finally:
+            stop.set()
+
+
 # ---------------------------------------------------------------------------------------------------
 # decode loop (evaluate.py:87-132)
 # ---------------------------------------------------------------------------------------------------
+LEAF_EXPAND_WIDTH = 8     # documents per ranked DocID expanded on the device; wider rows fall back to the host table
+
+
+def _expand_on_device(trie: DocidTrie, outputs, topk: int):
+    """(doc rows [B, topk, k] int64, counts [B, topk] int32, leaf ranges [B, topk, 2]) as host arrays; the expansion
+    itself (evaluate.py:118-128 smtid -> docids) runs on the device when the search results live there."""
+    leaf = outputs.leaf_ranges
+    if leaf.is_cuda:
+        docs, counts = trie.expand_ranges(leaf, LEAF_EXPAND_WIDTH)
+        return (docs.view(-1, topk, LEAF_EXPAND_WIDTH).cpu().numpy(), counts.view(-1, topk).cpu().numpy(),
+                leaf.view(-1, topk, 2).cpu().numpy())
+    return None, None, leaf.view(-1, topk, 2).numpy()
+
+
+def _docids_of(trie: DocidTrie, docs, counts, leaf, q: int, j: int) -> List[str]:
+    lo, hi = int(leaf[q, j, 0]), int(leaf[q, j, 1])
+    if hi <= lo:
+        return []
+    if counts is not None and counts[q, j] <= LEAF_EXPAND_WIDTH:
+        return [trie.docid_of_row(r) for r in docs[q, j, : counts[q, j]]]
+    return trie.docids_for_range(lo, hi)
+
+
 def constrained_decode_doc(model, dataloader, prefix_constrain_processor, smtid_to_docids, max_new_token, device,
                            out_dir, local_rank, topk=100, apply_log_softmax_for_scores=False, write=True):
     """smtid_to_docids: the reference's dict {"c1_.._cL": [docids]} or None to expand leaves from the trie."""
@@ -148,16 +220,23 @@ def constrained_decode_doc(model, dataloader, prefix_constrain_processor, smtid_
                             qid_to_rankdata[qid][docid] = rel_score if apply_log_softmax_for_scores \
                                 else rel_score * max_new_token
         else:   # same mapping from the trie's leaf table, no Python dict of 8.8M strings
-            leaf = outputs.leaf_ranges.view(-1, topk, 2).cpu().tolist()
-            for qid, ranges, rel_scores in zip(batch_qids, leaf, relevant_scores):
+            docs, counts, leaf = _expand_on_device(trie, outputs, topk)
+            for q, (qid, rel_scores) in enumerate(zip(batch_qids, relevant_scores)):
                 qid_to_rankdata[qid] = {}
-                for (lo, hi), rel_score in zip(ranges, rel_scores):
-                    if hi <= lo:
+                for j, rel_score in enumerate(rel_scores):
+                    docids = _docids_of(trie, docs, counts, leaf, q, j)
+                    if not docids:
                         print("smtid not in smtid_to_docid")
                         continue
-                    for docid in trie.docids_for_range(lo, hi):
+                    for docid in docids:
                         qid_to_rankdata[qid][docid] = rel_score if apply_log_softmax_for_scores \
                             else rel_score * max_new_token
+    if write == "gather":           # collective merge (replaces run_{rank}.json + the _2 task's file merge)
+        merged = gather_runs(qid_to_rankdata)
+        if merged is not None:
+            with open(os.path.join(out_dir, "run.json"), "w") as fout:
+                json.dump(merged, fout)
+        return merged if merged is not None else qid_to_rankdata
     if write:
         with open(os.path.join(out_dir, f"run_{local_rank}.json"), "w") as fout:
             json.dump(qid_to_rankdata, fout)
@@ -178,34 +257,46 @@ def ddp_setup():
         torch.distributed.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
 
 
+def load_docid_trie(docid_to_smtid_path: str, V: int, local_rank: int = 0, use_cache: bool = True) -> DocidTrie:
+    """docid_to_smtid.json -> DocidTrie (reference evaluate.py:400-446 builds three Python dict structures instead).
+    The file goes through the streaming C++ reader; the flattened trie is cached next to it as ``docid_trie.rb200``
+    (the counterpart of the reference's list_smtid_to_nextids.pkl, :404-432). The cache header carries a tag of the
+    json it was made from and is rebuilt when that does not match; it is written atomically by rank 0 only."""
+    cache = os.path.join(os.path.dirname(docid_to_smtid_path), "docid_trie.rb200")
+    tag = source_tag(docid_to_smtid_path)
+    dist = torch.distributed
+    if use_cache and os.path.exists(cache):
+        codes, docids = DocidTrie.read_json_codes(docid_to_smtid_path)
+        try:
+            trie = DocidTrie.load(cache, docids, expect_tag=tag)
+            if trie.L == codes.shape[1] and trie.V == V:
+                print("read flattened trie from {}".format(cache))
+                return trie
+        except (ValueError, _lib.RB200Error) as err:
+            print(f"ignoring {cache}: {err}")
+    trie = DocidTrie.from_json(docid_to_smtid_path, V)
+    if local_rank <= 0:
+        for i, n in enumerate(trie.level_counts()):
+            print(f"{i}-th step has {n:,} effective smtid ")
+        if use_cache and "experiments-full" in docid_to_smtid_path:       # same condition as the pickle (:405,428)
+            trie.save(cache, tag)
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier()
+    return trie
+
+
 def t5seq_aq_retrieve_docids(args, tokenizer=None):
     ddp_setup()
     model = T5SeqAQEncoder.from_pretrained(args.pretrained_path)
     model.eval()
-    with open(args.docid_to_smtid_path) as fin:
-        docid_to_smtids = json.load(fin)
     print(args.docid_to_smtid_path)
     V = model.config.decoder_vocab_sizes
     if len(set(V)) != 1:
         raise ValueError("not valid decoder_vocab_size")
-    cache = os.path.join(os.path.dirname(args.docid_to_smtid_path), "docid_trie.rb200")
-    docids = list(docid_to_smtids.keys())
-    if os.path.exists(cache):
-        print("read flattened trie from {}".format(cache))
-        trie = DocidTrie.load(cache, docids)
-    else:
-        pkl = os.path.join(os.path.dirname(args.docid_to_smtid_path), "list_smtid_to_nextids.pkl")
-        trie = DocidTrie.from_docid_to_smtid(docid_to_smtids, V[0])
-        if args.local_rank <= 0:
-            for i, n in enumerate(trie.level_counts()):
-                print(f"{i}-th step has {n:,} effective smtid ")
-            if "experiments-full" in args.docid_to_smtid_path and not os.path.exists(pkl):
-                trie.save(cache)
+    trie = load_docid_trie(args.docid_to_smtid_path, V[0], args.local_rank)
     prefix_constrain_processor = PrefixConstrainLogitProcessorFastSparse.from_trie(trie)
     max_new_token = args.max_new_token_for_docid
-    first = docid_to_smtids[docids[0]]
-    assert first[0] == -1, first
-    assert len(first) - 1 >= max_new_token, (first, max_new_token)
+    assert trie.L >= max_new_token, (trie.L, max_new_token)
     if args.local_rank <= 0:
         print("max_new_token: ", max_new_token)
         os.makedirs(args.out_dir, exist_ok=True)
@@ -228,9 +319,11 @@ def t5seq_aq_retrieve_docids(args, tokenizer=None):
         os.makedirs(out_dir, exist_ok=True)
         model.base_model.config.decoding = True
         # the trie was built on the full codes; shorter DocIDs (max_new_token < L) map to leaf ranges
-        constrained_decode_doc(model.base_model, dev_loader, prefix_constrain_processor, None, max_new_token,
+        feed = PrefetchLoader(dev_loader, depth=2, device=torch.device("cuda", local_rank))
+        constrained_decode_doc(model.base_model, feed, prefix_constrain_processor, None, max_new_token,
                                device=local_rank, out_dir=out_dir, local_rank=local_rank, topk=args.topk,
-                               apply_log_softmax_for_scores=args.apply_log_softmax_for_scores)
+                               apply_log_softmax_for_scores=args.apply_log_softmax_for_scores,
+                               write="gather" if getattr(args, "gather", False) and world > 1 else True)
 
 
 def merge_rank_runs(sub_runs: List[Dict]) -> Dict:
@@ -275,35 +368,111 @@ def t5seq_aq_retrieve_docids_2(args):
         evaluate_runs(args, q_paths)
 
 
+def pack_run(local_run: Dict) -> Dict[str, np.ndarray]:
+    """{qid: {docid: score}} -> flat arrays: qids int64 [n], lengths int64 [n], docids as bytes + offsets, scores f32.
+    Insertion order is kept (the merged run.json must list a query's documents in rank order)."""
+    qids = np.fromiter((int(q) for q in local_run), dtype=np.int64, count=len(local_run))
+    lens = np.fromiter((len(v) for v in local_run.values()), dtype=np.int64, count=len(local_run))
+    names = [str(d).encode() for v in local_run.values() for d in v]
+    scores = np.fromiter((float(x) for v in local_run.values() for x in v.values()), dtype=np.float64, count=len(names))
+    off = np.zeros(len(names) + 1, dtype=np.int64)
+    np.cumsum([len(b) for b in names], out=off[1:])
+    return {"qids": qids, "lens": lens, "off": off, "scores": scores,
+            "names": np.frombuffer(b"".join(names), dtype=np.uint8).copy()}
+
+
+def unpack_run(p: Dict[str, np.ndarray]) -> Dict:
+    run: Dict = {}
+    names, off, scores = p["names"].tobytes(), p["off"], p["scores"]
+    e = 0
+    for qid, n in zip(p["qids"].tolist(), p["lens"].tolist()):
+        d = run.setdefault(qid, {})
+        for _ in range(n):
+            d[names[off[e]: off[e + 1]].decode()] = float(scores[e])
+            e += 1
+    return run
+
+
 def gather_runs(local_run: Dict, group=None) -> Optional[Dict]:
-    """Collective replacement of the file merge: every rank contributes its {qid: {docid: score}} packed as
-    tensors; rank 0 returns the merged dict (others None). One all_gather of sizes + one of payloads."""
+    """Collective replacement of the reference's file merge (evaluate.py:130-132 run_{rank}.json, :489-526 merge):
+    every rank contributes its {qid: {docid: score}} as packed tensors over NCCL (gloo on CPU); rank 0 returns the
+    merged dict (duplicated queries from DistributedSampler padding collapse, as dict.update does there), the other
+    ranks None. One all_gather of the five array lengths and one all_gather_into_tensor of the byte payloads."""
     import torch.distributed as dist
     if not dist.is_initialized():
         return local_run
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    payload = np.frombuffer(pickle.dumps(local_run), dtype=np.uint8).copy()
     dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-    n = torch.tensor([payload.size], dtype=torch.int64, device=dev)
-    sizes = [torch.zeros_like(n) for _ in range(world)]
-    dist.all_gather(sizes, n, group=group)
-    mx = int(max(s.item() for s in sizes))
-    buf = torch.zeros(mx, dtype=torch.uint8, device=dev)
-    buf[: payload.size] = torch.from_numpy(payload).to(dev)
-    bufs = [torch.zeros_like(buf) for _ in range(world)]
-    dist.all_gather(bufs, buf, group=group)
+    p = pack_run(local_run)
+    order = ("qids", "lens", "off", "scores", "names")
+    blobs = [np.ascontiguousarray(p[k]).view(np.uint8).reshape(-1) for k in order]
+    sizes = torch.tensor([b.size for b in blobs], dtype=torch.int64, device=dev)
+    all_sizes = torch.zeros((world, len(order)), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(all_sizes, sizes, group=group)
+    all_sizes = all_sizes.cpu().numpy()
+    cap = int(all_sizes.sum(axis=1).max())
+    cap = (cap + 15) // 16 * 16
+    payload = torch.zeros(cap, dtype=torch.uint8, device=dev)
+    flat = np.concatenate(blobs) if blobs else np.zeros(0, np.uint8)
+    payload[: flat.size] = torch.from_numpy(flat).to(dev)
+    gathered = torch.empty(world * cap, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(gathered, payload, group=group)
     if rank != 0:
         return None
-    return merge_rank_runs([pickle.loads(b[: int(s.item())].cpu().numpy().tobytes()) for b, s in zip(bufs, sizes)])
+    gathered = gathered.cpu().numpy().reshape(world, cap)
+    dtypes = {"qids": np.int64, "lens": np.int64, "off": np.int64, "scores": np.float64, "names": np.uint8}
+    subs = []
+    for r in range(world):
+        o, parts = 0, {}
+        for k, n in zip(order, all_sizes[r].tolist()):
+            parts[k] = gathered[r, o: o + n].copy().view(dtypes[k])
+            o += n
+        subs.append(unpack_run(parts))
+    return merge_rank_runs(subs)
+
+
+def gather_ranked_lists(qids: torch.Tensor, doc_rows: torch.Tensor, scores: torch.Tensor, group=None):
+    """The per-batch collective of the data path: all_gather of the packed ranked lists
+    ``doc_rows`` int64 [B_loc, nb] (+ ``scores`` fp32 [B_loc, nb], ``qids`` int64 [B_loc]) over NCCL. Every rank gets
+    ([world*B_loc], [world*B_loc, nb], [world*B_loc, nb]); rows of padded (duplicated) queries are dropped by the
+    caller with ``unique_queries``. Without a process group the inputs are returned."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return qids, doc_rows, scores
+    world = dist.get_world_size(group)
+    B, nb = doc_rows.shape
+    # one packed int64 buffer per rank: [qid | doc rows | score bits]
+    packed = torch.empty((B, 1 + 2 * nb), dtype=torch.int64, device=doc_rows.device)
+    packed[:, 0] = qids.to(doc_rows.device)
+    packed[:, 1: 1 + nb] = doc_rows
+    packed[:, 1 + nb:] = scores.to(torch.float32).contiguous().view(torch.int32).to(torch.int64)
+    out = torch.empty((world * B, 1 + 2 * nb), dtype=torch.int64, device=doc_rows.device)
+    dist.all_gather_into_tensor(out, packed, group=group)
+    # DistributedSampler order: global index i*world + rank  <->  row rank*B + i
+    out = out.view(world, B, -1).transpose(0, 1).reshape(world * B, -1)
+    return out[:, 0], out[:, 1: 1 + nb], out[:, 1 + nb:].to(torch.int32).view(torch.float32)
+
+
+def unique_queries(qids: torch.Tensor, n_queries: int) -> torch.Tensor:
+    """Row indices that keep the first occurrence of every query (DistributedSampler pads by wrapping around)."""
+    return torch.arange(min(n_queries, qids.shape[0]), device=qids.device)
 
 
 def mrr_k(run: Dict, qrel: Dict, k: int = 10) -> float:
-    """MRR@k without pytrec_eval (reference utils/metrics.py:18-25 truncates the run to top-k by score first)."""
+    """MRR@k as reference utils/metrics.py:9-25 computes it, without pytrec_eval (not installed): ``truncate_run``
+    keeps the first k documents of a stable sort by score (descending); pytrec_eval's ``recip_rank`` then ranks those
+    by score with ties broken by docid in DESCENDING lexicographic order (trec_eval's sort), looks at the queries that
+    are in both the run and the qrel, and the mean is taken over those queries only."""
     total, n = 0.0, 0
-    for qid, rel in qrel.items():
-        ranked = sorted(run.get(qid, {}).items(), key=lambda kv: kv[1], reverse=True)[:k]
+    for qid, docs in run.items():
+        rel = qrel.get(qid)
+        if rel is None:
+            continue
+        top = sorted(docs.items(), key=lambda kv: kv[1], reverse=True)[:k]
+        top.sort(key=lambda kv: kv[0], reverse=True)            # docid descending ...
+        top.sort(key=lambda kv: kv[1], reverse=True)            # ... within equal scores (stable)
         rr = 0.0
-        for i, (docid, _) in enumerate(ranked):
+        for i, (docid, _) in enumerate(top):
             if rel.get(docid, 0) > 0:
                 rr = 1.0 / (i + 1)
                 break
@@ -343,15 +512,15 @@ def constrained_decode_smtid(model, dataloader, prefix_constrain_processor, smti
         batch_qids = batch["id"].cpu().tolist()
         str_smtids = convert_ptsmtids_to_strsmtid(outputs.sequences.view(-1, topk, max_new_token + 1), max_new_token)
         relevant_scores = outputs.sequences_scores.view(-1, topk).cpu().tolist()
-        leaf = outputs.leaf_ranges.view(-1, topk, 2).cpu().tolist()
-        for qid, ranked_smtids, rel_scores, ranges in zip(batch_qids, str_smtids, relevant_scores, leaf):
+        docs, counts, leaf = _expand_on_device(trie, outputs, topk)
+        for q, (qid, ranked_smtids, rel_scores) in enumerate(zip(batch_qids, str_smtids, relevant_scores)):
             qid_to_rankdata[qid] = {}
-            for smtid, rel_score, (lo, hi) in zip(ranked_smtids, rel_scores, ranges):
+            for j, (smtid, rel_score) in enumerate(zip(ranked_smtids, rel_scores)):
                 qid_to_rankdata[qid][smtid] = {}
                 if smtid_to_docids is not None:
                     docids = smtid_to_docids.get(smtid, [])
                 else:
-                    docids = trie.docids_for_range(lo, hi)
+                    docids = _docids_of(trie, docs, counts, leaf, q, j)
                 for docid in docids:
                     qid_to_rankdata[qid][smtid][docid] = rel_score if apply_log_softmax_for_scores \
                         else rel_score * max_new_token
@@ -367,21 +536,14 @@ def t5seq_aq_get_qid_to_smtid_rankdata(args, tokenizer=None):
     ddp_setup()
     model = T5SeqAQEncoder.from_pretrained(args.pretrained_path)
     model.eval()
-    with open(args.docid_to_smtid_path) as fin:
-        docid_to_smtids = json.load(fin)
     V = model.config.decoder_vocab_sizes
     if len(set(V)) == 2:
         raise NotImplementedError
     if len(set(V)) != 1:
         raise ValueError("not valid decoder_vocab_size")
-    docids = list(docid_to_smtids.keys())
-    trie = DocidTrie.from_docid_to_smtid(docid_to_smtids, V[0])
-    if args.local_rank <= 0:
-        for i, n in enumerate(trie.level_counts()):
-            print(f"{i}-th step has {n:,} effective smtid ")
+    trie = load_docid_trie(args.docid_to_smtid_path, V[0], args.local_rank)     # (asserts smtids[0] == -1)
     prefix_constrain_processor = PrefixConstrainLogitProcessorFastSparse.from_trie(trie)
     assert args.max_new_token in [4, 8, 16, 32], args.max_new_token
-    assert docid_to_smtids[docids[0]][0] == -1
     if args.local_rank <= 0:
         os.makedirs(args.out_dir, exist_ok=True)
     world = torch.distributed.get_world_size() if torch.distributed.is_initialized() else 1
@@ -396,7 +558,8 @@ def t5seq_aq_get_qid_to_smtid_rankdata(args, tokenizer=None):
     model.to(local_rank)
     print("out_dir: ", args.out_dir)
     model.base_model.config.decoding = True
-    return constrained_decode_smtid(model.base_model, dev_loader, prefix_constrain_processor, None, args.max_new_token,
+    feed = PrefetchLoader(dev_loader, depth=2, device=torch.device("cuda", local_rank))
+    return constrained_decode_smtid(model.base_model, feed, prefix_constrain_processor, None, args.max_new_token,
                                     device=local_rank, out_dir=args.out_dir, local_rank=local_rank, topk=args.topk,
                                     apply_log_softmax_for_scores=args.apply_log_softmax_for_scores)
 
@@ -457,6 +620,9 @@ def get_args(argv=None):
     ap.add_argument("--train_query_dir", type=str, default=None)
     ap.add_argument("--apply_log_softmax_for_scores", action="store_true")
     ap.add_argument("--local_rank", type=int, default=int(os.environ.get("LOCAL_RANK", -1)))
+    ap.add_argument("--gather", action="store_true",
+                    help="merge the per-rank runs with one NCCL gather and let rank 0 write run.json directly "
+                         "(instead of run_{rank}.json files + the _2 merge task)")
     ap.add_argument("--num_ranks", type=int, default=0, help="run_*.json files expected by the merge task "
                                                               "(default: torch.cuda.device_count() like the reference)")
     return ap.parse_args(argv)

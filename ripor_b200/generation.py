@@ -83,8 +83,8 @@ def generate_for_constrained_prefix_beam_search(model, valid_smtids, inputs: Opt
         max_new_tokens = max_length - 1                              # generation.py:153-154
     if num_return_sequences > num_beams:
         raise ValueError("`num_return_sequences` has to be smaller or equal to `num_beams`.")   # :216-217
-    if num_beams < 2:
-        raise ValueError("constrained retrieval runs in beam mode: num_beams must be > 1")
+    if num_beams < 2:    # HF 4.17 BeamSearchScorer.__init__ (constructed at generation.py:222) refuses num_beams <= 1
+        raise ValueError(f"`num_beams` has to be an integer strictly greater than 1, but is {num_beams}.")
     base = getattr(model, "base_model", model)
     trie: DocidTrie = valid_smtids.trie
     B, S = input_ids.shape
@@ -133,12 +133,18 @@ def generate_for_constrained_prefix_beam_search(model, valid_smtids, inputs: Opt
         # element (4-byte read) and redo the batch in tf32x3; explicit fp16x3 hands the NaNs to the caller
         if auto and mode == "fp16x3" and bool(torch.isnan(scores[:1]).item()):
             base.fp16_ok = False
+            base.drop_engine("fp16x3")           # do not keep two sets of packed weights and workspaces in HBM
             continue
         break
     out = BeamSearchEncoderDecoderOutput(seqs, scores, leaf)
     out.gpu_launches = int(L.rb200_engine_last_launch_count(engine.h))
     out.precision = mode
-    out.forced_tail_from = int(L.rb200_engine_last_tail_step(engine.h))   # -1: stepwise to the end
+    out.forced_tail_from = int(L.rb200_engine_last_tail_step(engine.h))   # -1: every query stepped to the end
+    hist = (C.c_int32 * 33)()
+    rows = C.c_int64()
+    _lib.check(L.rb200_engine_last_freeze_histogram(engine.h, hist, 33, C.byref(rows)))
+    out.frozen_at_step = list(hist)[: max_new_tokens + 1]                # queries frozen after t steps
+    out.forced_tail_rows = int(rows.value)
     if return_dict_in_generate is False:
         return seqs
     return out

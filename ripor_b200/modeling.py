@@ -20,6 +20,37 @@ from . import _lib
 from .synthetic import T5Dims
 
 
+class T5GenRetModelOutput:
+    """reference t5_generative_retriever.py:40-43 (a Seq2SeqLMOutput with ``logits`` being a list per position)."""
+
+    def __init__(self, logits=None, past_key_values=None, decoder_last_hidden_state=None,
+                 encoder_last_hidden_state=None):
+        self.loss = None
+        self.logits = logits
+        self.past_key_values = past_key_values
+        self.decoder_last_hidden_state = decoder_last_hidden_state
+        self.decoder_hidden_states = None
+        self.decoder_attentions = None
+        self.cross_attentions = None
+        self.encoder_last_hidden_state = encoder_last_hidden_state
+        self.encoder_hidden_states = None
+        self.encoder_attentions = None
+
+    def __getitem__(self, k):
+        return getattr(self, k)
+
+
+def _device_view(ptr: int, nbytes: int, device: torch.device) -> torch.Tensor:
+    """uint8 tensor aliasing a raw device pointer handed out by the C ABI (valid until the next engine call)."""
+    class _Holder:
+        __cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 2}
+    return torch.as_tensor(_Holder(), device=device)
+
+
+def _round_up(x: int, m: int) -> int:
+    return -(-x // m) * m
+
+
 class T5forDocIDConfig:
     """Fields of the reference config that the retrieval path reads (config.json of save_pretrained)."""
 
@@ -71,6 +102,7 @@ class _Engine:
         if len(set(cfg.decoder_vocab_sizes)) != 1:
             raise ValueError("not valid decoder_vocab_size")          # reference evaluate.py:433-436
         self.key = (device, max_batch, max_beams, max_src_len, precision)
+        self.resizes = 0
         ec = _lib.EngineConfig(cfg.d_model, cfg.num_heads, cfg.d_kv, cfg.d_ff, cfg.num_layers,
                                cfg.num_decoder_layers, cfg.vocab_size, cfg.relative_attention_num_buckets,
                                cfg.relative_attention_max_distance, cfg.layer_norm_epsilon,
@@ -93,12 +125,30 @@ class _Engine:
         _lib.check(L.rb200_engine_finalize_weights(self.h, stream))
 
     def __del__(self):
+        self.free()
+
+    def free(self):
         try:
             if getattr(self, "h", None):
                 _lib.lib().rb200_engine_free(self.h)
                 self.h = None
         except Exception:
             pass
+
+    @property
+    def caps(self):
+        return self.key[1:4]
+
+    def rows(self, caps=None):
+        mb, nb, ms = caps or self.caps
+        return mb * nb
+
+    def resize(self, max_batch: int, max_beams: int, max_src_len: int) -> None:
+        """New workspace capacities; the packed weights are kept (rb200_engine_resize)."""
+        _lib.check(_lib.lib().rb200_engine_resize(self.h, max_batch, max_beams, max_src_len))
+        self.key = (self.key[0], max_batch, max_beams, max_src_len, self.key[4])
+        self.resizes += 1
+        self.host_out_key = None
 
 
 class T5ForDocIDGeneration:
@@ -142,18 +192,125 @@ class T5ForDocIDGeneration:
         if precision == "auto":
             raise ValueError("resolve 'auto' with resolve_precision() first")
         dev = self._device if self._device is not None else torch.cuda.current_device()
+        # Source lengths come in buckets of 32 positions (the loader pads every batch to its own longest row,
+        # dataloader.py:62-79), and an engine serves every batch <= max_batch, num_beams <= max_beams, S <= max_src_len.
+        # When a call does not fit, only the workspaces are re-allocated (the packed weights stay): to the union of the
+        # old and new shapes if that is not much bigger than either, else to the new shape.
+        src_cap = _round_up(max(src_len, 8), 32)
         e = self._engines.get(precision)
-        if e is not None:
-            d0, mb, nb, ms, pr = e.key
-            if d0 == dev and nb == num_beams and mb >= batch and ms >= src_len:
-                return e
-            del self._engines[precision]
-            del e
-            torch.cuda.synchronize()
+        if e is not None and e.key[0] != dev:
+            self.drop_engine(precision)
+            e = None
+        if e is None:
+            with torch.cuda.device(dev):
+                e = self._engines[precision] = _Engine(self.config, self._weights, dev, batch, num_beams, src_cap,
+                                                       precision)
+            return e
+        mb, nb, ms = e.caps
+        if mb >= batch and nb >= num_beams and ms >= src_len:
+            return e
+        union = (max(mb, batch), max(nb, num_beams), max(ms, src_cap))
+        exact = (batch, num_beams, max(ms, src_cap))
+        new = union if union[0] * union[1] <= 2 * max(mb * nb, batch * num_beams) else exact
         with torch.cuda.device(dev):
-            self._engines[precision] = _Engine(self.config, self._weights, dev, batch, num_beams, max(src_len, 8),
-                                               precision)
-        return self._engines[precision]
+            torch.cuda.synchronize()
+            e.resize(*new)
+        return e
+
+    def drop_engine(self, precision: str) -> None:
+        """Free the engine of one precision mode (e.g. fp16x3 after the automatic fall-back to tf32x3)."""
+        e = self._engines.pop(precision, None)
+        if e is not None:
+            torch.cuda.synchronize()
+            e.free()
+
+    # -- the reference's model forward (t5_generative_retriever.py:295-450), teacher-forced on the engine -----------
+    def forward(self, input_ids=None, attention_mask=None, decoder_input_ids=None, encoder_outputs=None,
+                return_dict=True, precision: Optional[str] = None, **unused):
+        """``input_ids`` / ``attention_mask`` [bz, S]; ``decoder_input_ids`` [bz, T] whose column 0 is the decoder start
+        token (0 or -1, reference :204) and whose columns 1.. are DocID codes. Returns ``T5GenRetModelOutput`` with
+        ``decoder_last_hidden_state`` [bz, T, d_model], ``encoder_last_hidden_state`` [bz, S, d_model] and, when
+        ``config.decoding`` is set, ``logits`` = list of T tensors [bz, V] (position i against the i-th output table,
+        :250-262). ``past_key_values`` is None: the engine keeps its own KV cache (the reference never consumed
+        its cache either, SURVEY.md finding 4)."""
+        if input_ids is None or attention_mask is None:
+            raise NotImplementedError("the engine runs its own encoder: pass input_ids and attention_mask "
+                                      "(encoder_outputs alone is not supported)")
+        if decoder_input_ids is None:
+            raise ValueError("decoder_input_ids is required (the retrieval path always decodes)")
+        dec = decoder_input_ids.to(torch.int64)
+        assert dec.dim() == 2 and dec.shape[0] == input_ids.shape[0]
+        assert int(dec[0, 0]) in (-1, 0), dec[0, 0]                      # reference :204
+        T = dec.shape[1]
+        assert T <= len(self.config.decoder_vocab_sizes), "seq_length <= num_decoder_embeds (reference :201)"
+        tokens = torch.zeros((dec.shape[0], T), dtype=torch.int32)
+        tokens[:, : T - 1] = dec[:, 1:].to(torch.int32).cpu()          # token p feeds position p + 1
+        out = self._forced(input_ids, attention_mask, tokens, 1, want_logits=bool(self.config.decoding),
+                           want_hidden=True, want_scores=False, precision=precision)
+        logits = None
+        if out["logits"] is not None:
+            logits = [out["logits"][p] for p in range(T)]
+        res = T5GenRetModelOutput(logits=logits, past_key_values=None,
+                                  decoder_last_hidden_state=out["hidden"].permute(1, 0, 2).contiguous(),
+                                  encoder_last_hidden_state=out["encoder"])
+        if not return_dict:
+            return (res.logits, res.decoder_last_hidden_state, res.encoder_last_hidden_state)
+        return res
+
+    __call__ = forward
+
+    def prepare_inputs_for_generation(self, input_ids, past_key_values=None, attention_mask=None, head_mask=None,
+                                      decoder_head_mask=None, cross_attn_head_mask=None, use_cache=None,
+                                      encoder_outputs=None, **kwargs):
+        """reference :452-479. (There ``past`` never reaches ``past_key_values``, so the whole prefix is fed.)"""
+        return {"decoder_input_ids": input_ids, "past_key_values": past_key_values,
+                "encoder_outputs": encoder_outputs, "attention_mask": attention_mask, "use_cache": use_cache}
+
+    @staticmethod
+    def _reorder_cache(past, beam_idx):
+        """reference :484-512. The engine addresses its KV cache through a beam ancestry table instead of copying
+        it, so there is nothing to reorder; kept for callers that drive their own loop."""
+        return past
+
+    def _forced(self, input_ids, attention_mask, tokens: torch.Tensor, rows_per_query: int, want_logits: bool,
+                want_hidden: bool, want_scores: bool, precision: Optional[str] = None):
+        """rb200_engine_forward: teacher-forced decoder pass. tokens int32 [B*rows_per_query, T]."""
+        B, S = input_ids.shape
+        R, T = tokens.shape
+        assert R == B * rows_per_query
+        L = _lib.lib()
+        while True:
+            mode = self.resolve_precision(precision)
+            try:
+                eng = self.get_engine(B, rows_per_query, S, mode)
+            except ValueError as err:
+                if (precision or self.precision) == "auto" and mode == "fp16x3" and "fp16 range" in str(err):
+                    self.fp16_ok = False
+                    continue
+                raise
+            dev = torch.device("cuda", eng.key[0])
+            with torch.cuda.device(dev):
+                ids = input_ids.to(device=dev, dtype=torch.int64).contiguous()
+                mask = attention_mask.to(device=dev, dtype=torch.int64).contiguous()
+                tok = tokens.to(device=dev, dtype=torch.int32).contiguous()
+                V, d = self.config.decoder_vocab_sizes[0], self.config.d_model
+                logits = torch.empty((T, R, V), dtype=torch.float32, device=dev) if want_logits else None
+                hidden = torch.empty((T, R, d), dtype=torch.float32, device=dev) if want_hidden else None
+                scores = torch.empty((R,), dtype=torch.float32, device=dev) if want_scores else None
+                _lib.check(L.rb200_engine_forward(
+                    eng.h, ids.data_ptr(), mask.data_ptr(), B, S, rows_per_query, tok.data_ptr(), T,
+                    logits.data_ptr() if want_logits else None, hidden.data_ptr() if want_hidden else None,
+                    scores.data_ptr() if want_scores else None, _lib.stream_ptr()))
+                p = C.c_void_p()
+                _lib.check(L.rb200_engine_encoder_states(eng.h, C.byref(p)))
+                enc = _device_view(p.value, B * S * d * 4, dev).view(torch.float32).view(B, S, d).clone()
+                probe = scores if want_scores else (logits if want_logits else None)
+                if (precision or self.precision) == "auto" and mode == "fp16x3" and probe is not None and \
+                        bool(torch.isnan(probe.reshape(-1)[:1]).item()):
+                    self.fp16_ok = False                                 # fp16 range overflow: redo in tf32x3
+                    self.drop_engine("fp16x3")
+                    continue
+            return {"logits": logits, "hidden": hidden, "scores": scores, "encoder": enc, "precision": mode}
 
     def resolve_precision(self, precision: Optional[str] = None) -> str:
         """'auto' -> 'fp16x3' until an fp16 range overflow has been seen on this model, then 'tf32x3'."""
@@ -220,6 +377,45 @@ class T5SeqAQEncoder:
     def to(self, device):
         self.base_model.to(device)
         return self
+
+    def query_encode(self, **inputs):
+        """reference :786-792."""
+        text_reps = self.base_model(**inputs).decoder_last_hidden_state
+        assert text_reps.size(1) - 1 == 0
+        return text_reps[:, 0, :]
+
+    def output_table(self, i: int) -> torch.Tensor:
+        sd = self.base_model.state_dict()
+        name = "list_decoder_embeds" if self.config.shared_output_input_embeds else "list_output_embeds"
+        return sd[f"{name}.{i}.weight"]
+
+    def decode(self, text_encodings: torch.Tensor, summation: bool = False) -> torch.Tensor:
+        """reference :812-832: rows of the per-position output tables [bz, smtid_length, d_model]."""
+        embeds = [self.output_table(i).to(text_encodings.device)[text_encodings[:, i]].unsqueeze(1)
+                  for i in range(text_encodings.size(1))]
+        text_embeds = torch.cat(embeds, dim=1)
+        return text_embeds.sum(dim=1) if summation else text_embeds
+
+    def rerank_forward(self, **inputs) -> torch.Tensor:
+        """reference :794-798: sum over positions of <decoder hidden state, output embedding of the doc's code> = the
+        teacher-forced sum of the doc's logits; computed inside the engine (rb200_engine_forward scores)."""
+        tq = inputs["tokenized_query"]
+        doc = inputs["doc_encoding"].to(torch.int64)
+        dec = tq["decoder_input_ids"].to(torch.int64)
+        assert dec.shape == doc.shape, (dec.shape, doc.shape)
+        assert torch.equal(dec[:, 1:].cpu(), doc[:, :-1].cpu()), \
+            "decoder_input_ids must be the start token followed by the doc's first L-1 codes"
+        out = self.base_model._forced(tq["input_ids"], tq["attention_mask"], doc.to(torch.int32).cpu(), 1,
+                                      want_logits=False, want_hidden=False, want_scores=True)
+        return out["scores"]
+
+    def score_docids(self, input_ids, attention_mask, codes: torch.Tensor) -> torch.Tensor:
+        """Engine extension of rerank_forward: n candidate DocIDs per query share one encoder pass.
+        codes int [B, n, L] -> scores fp32 [B, n]."""
+        B, n, L = codes.shape
+        out = self.base_model._forced(input_ids, attention_mask, codes.reshape(B * n, L).to(torch.int32).cpu(), n,
+                                      want_logits=False, want_hidden=False, want_scores=True)
+        return out["scores"].view(B, n)
 
     def save_pretrained(self, save_dir):
         self.base_model.save_pretrained(save_dir)

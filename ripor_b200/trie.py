@@ -16,6 +16,41 @@ import numpy as np
 from . import _lib
 
 
+class DocidStrings:
+    """Read-only list of the docid strings of docid_to_smtid.json in file order, kept as one byte buffer + offsets
+    (8.8 M Python str objects would cost ~0.6 GB and seconds to build; the output mapping touches a few thousand)."""
+
+    def __init__(self, key_bytes: np.ndarray, offsets: np.ndarray):
+        self._bytes, self._off = key_bytes, offsets
+
+    def __len__(self) -> int:
+        return len(self._off) - 1
+
+    def __getitem__(self, i: int) -> str:
+        if i < 0:
+            i += len(self)
+        return self._bytes[self._off[i]: self._off[i + 1]].tobytes().decode("utf-8")
+
+    def __iter__(self):
+        return (self[i] for i in range(len(self)))
+
+
+def source_tag(path: str) -> int:
+    """64-bit tag of a source file (size, mtime, first/last 64 KB) stored in the trie cache header, so that a cache
+    made from another docid_to_smtid.json is rebuilt instead of silently mapping beams to the wrong documents."""
+    import hashlib
+    import os
+    st = os.stat(path)
+    h = hashlib.blake2b(digest_size=8)
+    h.update(f"{st.st_size}:{st.st_mtime_ns}".encode())
+    with open(path, "rb") as f:
+        h.update(f.read(65536))
+        if st.st_size > 65536:
+            f.seek(max(st.st_size - 65536, 0))
+            h.update(f.read(65536))
+    return int.from_bytes(h.digest(), "little") or 1
+
+
 class DocidTrie:
     def __init__(self, handle: C.c_void_p, docids: Optional[List[str]] = None):
         self._h = handle
@@ -59,9 +94,44 @@ class DocidTrie:
         return cls.from_codes(codes, V, docids)
 
     @classmethod
-    def from_json(cls, path: str, V: int, max_new_token_for_docid: Optional[int] = None) -> "DocidTrie":
-        with open(path) as f:
-            return cls.from_docid_to_smtid(json.load(f), V, max_new_token_for_docid)
+    def from_json(cls, path: str, V: int, max_new_token_for_docid: Optional[int] = None, n_threads: int = 0
+                  ) -> "DocidTrie":
+        """docid_to_smtid.json -> trie through the streaming C++ reader (rb200_docid_json_open): no Python dict of
+        8.8 M lists (the reference's ujson.load + dict walk, evaluate.py:400-446)."""
+        L = _lib.lib()
+        tab = C.c_void_p()
+        _lib.check(L.rb200_docid_json_open(path.encode(), int(max_new_token_for_docid or 0), C.byref(tab)))
+        try:
+            h = C.c_void_p()
+            _lib.check(L.rb200_trie_build_from_table(tab, V, n_threads, C.byref(h)))
+            n, key_bytes = C.c_int64(), C.c_int64()
+            _lib.check(L.rb200_docid_json_info(tab, C.byref(n), None, None, C.byref(key_bytes)))
+            kb, ko = C.c_void_p(), C.c_void_p()
+            _lib.check(L.rb200_docid_json_keys(tab, C.byref(kb), C.byref(ko)))
+            keys = np.ctypeslib.as_array(C.cast(kb, C.POINTER(C.c_uint8)), shape=(max(key_bytes.value, 1),)).copy()
+            offs = np.ctypeslib.as_array(C.cast(ko, C.POINTER(C.c_int64)), shape=(n.value + 1,)).copy()
+        finally:
+            L.rb200_docid_json_free(tab)
+        return cls(h, DocidStrings(keys, offs))
+
+    @staticmethod
+    def read_json_codes(path: str, max_new_token_for_docid: Optional[int] = None):
+        """(codes int32 [N, L], DocidStrings) of a docid_to_smtid.json, via the C++ reader."""
+        L = _lib.lib()
+        tab = C.c_void_p()
+        _lib.check(L.rb200_docid_json_open(path.encode(), int(max_new_token_for_docid or 0), C.byref(tab)))
+        try:
+            n, ln, key_bytes = C.c_int64(), C.c_int32(), C.c_int64()
+            _lib.check(L.rb200_docid_json_info(tab, C.byref(n), C.byref(ln), None, C.byref(key_bytes)))
+            cp, kb, ko = C.c_void_p(), C.c_void_p(), C.c_void_p()
+            _lib.check(L.rb200_docid_json_codes(tab, C.byref(cp)))
+            _lib.check(L.rb200_docid_json_keys(tab, C.byref(kb), C.byref(ko)))
+            codes = np.ctypeslib.as_array(C.cast(cp, C.POINTER(C.c_int32)), shape=(n.value, ln.value)).copy()
+            keys = np.ctypeslib.as_array(C.cast(kb, C.POINTER(C.c_uint8)), shape=(max(key_bytes.value, 1),)).copy()
+            offs = np.ctypeslib.as_array(C.cast(ko, C.POINTER(C.c_int64)), shape=(n.value + 1,)).copy()
+        finally:
+            L.rb200_docid_json_free(tab)
+        return codes, DocidStrings(keys, offs)
 
     @classmethod
     def from_list_smtid_to_nextids(cls, list_smtid_to_nextids: List[Dict[str, Iterable[int]]], V: int) -> "DocidTrie":
@@ -76,13 +146,21 @@ class DocidTrie:
         return cls.from_codes(np.asarray(rows, dtype=np.int64).reshape(len(rows), len(list_smtid_to_nextids)), V)
 
     @classmethod
-    def load(cls, path: str, docids: Optional[List[str]] = None) -> "DocidTrie":
-        h = C.c_void_p()
-        _lib.check(_lib.lib().rb200_trie_load(path.encode(), C.byref(h)))
-        return cls(h, docids)
+    def load(cls, path: str, docids: Optional[List[str]] = None, expect_tag: Optional[int] = None) -> "DocidTrie":
+        """Read a trie cache. ``expect_tag`` (see ``source_tag``) and ``docids`` are checked against the header: a
+        cache made from another source raises ValueError (callers rebuild)."""
+        h, tag = C.c_void_p(), C.c_uint64()
+        _lib.check(_lib.lib().rb200_trie_load_tagged(path.encode(), C.byref(tag), C.byref(h)))
+        t = cls(h, docids)
+        if expect_tag is not None and tag.value != expect_tag:
+            raise ValueError(f"{path} was built from another docid_to_smtid.json (tag {tag.value:#x} != {expect_tag:#x})")
+        if docids is not None and len(docids) != t.n_docs:
+            raise ValueError(f"{path} holds {t.n_docs} documents, the docid table {len(docids)}")
+        return t
 
-    def save(self, path: str) -> None:
-        _lib.check(_lib.lib().rb200_trie_save(self._h, path.encode()))
+    def save(self, path: str, tag: int = 0) -> None:
+        """Atomic (temporary file + rename) write of the cache with the source tag in its header."""
+        _lib.check(_lib.lib().rb200_trie_save_tagged(self._h, path.encode(), tag))
 
     def __del__(self):
         try:
@@ -125,6 +203,23 @@ class DocidTrie:
         out = torch.empty((R, self.V), dtype=torch.float64)
         _lib.check(_lib.lib().rb200_trie_mask_host(self._h, ids.data_ptr(), R, T, out.data_ptr()))
         return out
+
+    def expand_ranges(self, leaf_ranges, max_docs_per_row: int = 8):
+        """Device-side smtid -> docids mapping (rb200_trie_leaf_expand). leaf_ranges: CUDA int32 [n, 2] as returned by
+        the search; returns (doc rows int64 [n, k] in json order padded with -1, true counts int32 [n])."""
+        import torch
+        assert leaf_ranges.is_cuda and leaf_ranges.dtype == torch.int32
+        lr = leaf_ranges.contiguous()
+        n = lr.shape[0]
+        docs = torch.empty((n, max_docs_per_row), dtype=torch.int64, device=lr.device)
+        counts = torch.empty((n,), dtype=torch.int32, device=lr.device)
+        self.upload(lr.device.index or 0)
+        _lib.check(_lib.lib().rb200_trie_leaf_expand(self._h, lr.data_ptr(), n, max_docs_per_row, docs.data_ptr(),
+                                                     counts.data_ptr(), _lib.stream_ptr()))
+        return docs, counts
+
+    def docid_of_row(self, row: int) -> str:
+        return str(int(row)) if self.docids is None else self.docids[int(row)]
 
     def leaf_rows(self, leaf: int) -> np.ndarray:
         ptr, n = C.c_void_p(), C.c_int64()
