@@ -165,8 +165,11 @@ def beam_search_oracle(step_logits: Callable[[torch.Tensor, Optional[torch.Tenso
         beam_idx = out["next_beam_indices"]
         input_ids = torch.cat([input_ids[beam_idx, :], out["next_beam_tokens"].unsqueeze(-1)], dim=-1)  # :511
         if trace is not None:
+            # cut_gap: distance between the last candidate that stays in the beam and the first one that does not -
+            # a gap below the arithmetic noise of an fp32 forward pass is a near-tie, not a parity question
             trace.append({"beam_scores": beam_scores.clone(), "beam_idx": beam_idx.clone(),
-                          "tokens": out["next_beam_tokens"].clone(), "processed": processed.clone()})
+                          "tokens": out["next_beam_tokens"].clone(), "processed": processed.clone(),
+                          "cut_gap": (nxt[:, nb - 1] - nxt[:, nb]).clone()})
     fin = scorer.finalize(input_ids, beam_scores, next_tokens, next_indices, max_length=L + 1)
     return fin["sequences"], fin["sequence_scores"]
 

@@ -866,17 +866,128 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
 // the relative position bias applied to the score fragments.
 constexpr int kTailMmaWarpBytes = 4 * 32 * kKLd * 2;          // K hi | K lo | V hi | V lo
 
-__global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(TailAttnArgs a, ActOut ctx) {
+// The T queries of one (frozen row, head) task as 16-row m16n8k16 tiles against the staged fp16 K/V planes of its
+// lineage: tile row q = query index (position t + q); causal mask and relative position bias on the score fragments.
+__device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const ActOut& ctx, const __half* k_hi,
+                                                 const __half* k_lo, const __half* v_hi, const __half* v_lo, int rp,
+                                                 int h, int t, int T, bool& bad) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
+  const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
+  const int vrow = (lane & 7) + 8 * ((lane >> 3) & 1), vcol = 8 * (lane >> 4);   // ldmatrix row of this lane
+  const int inner = a.H * 64, L = a.L;
+  // ---- the T queries as 16-row tiles: tile row q = query index (position t + q) --------------------------------
+  for (int tile = 0; tile * 16 < T; ++tile) {
+    const int q0 = tile * 16 + g, q1 = q0 + 8;
+    const float* qr0 = a.qkv + ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+    const float* qr1 = a.qkv + ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+    float sacc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) sacc[nt][u] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float2 x0 = *reinterpret_cast<const float2*>(qr0 + kk * 16), x1 = *reinterpret_cast<const float2*>(qr1 + kk * 16);
+      const float2 x2 = *reinterpret_cast<const float2*>(qr0 + kk * 16 + 8);
+      const float2 x3 = *reinterpret_cast<const float2*>(qr1 + kk * 16 + 8);
+      uint32_t ah[4], al[4];
+      split_h2(x0.x, x0.y, ah[0], al[0], bad);
+      split_h2(x1.x, x1.y, ah[1], al[1], bad);
+      split_h2(x2.x, x2.y, ah[2], al[2], bad);
+      split_h2(x3.x, x3.y, ah[3], al[3], bad);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t4;
+        const uint32_t bh0 = kh32[o0], bh1 = kh32[o0 + 4], bl0 = kl32[o0], bl1 = kl32[o0 + 4];
+        mma_f16(sacc[nt], al, bh0, bh1);
+        mma_f16(sacc[nt], ah, bl0, bl1);
+        mma_f16(sacc[nt], ah, bh0, bh1);
+      }
+    }
+    // causal mask + relative position bias: row q sits at position t + q and sees keys p <= t + q
+    const int pq0 = t + q0, pq1 = t + q1;
+    const float* bias_h = a.bias + h * L;
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        const int p = nt * 8 + 2 * t4 + w;
+        sacc[nt][w] = (p <= pq0 && q0 < T) ? sacc[nt][w] + __ldg(bias_h + (pq0 - p)) : -INFINITY;
+        sacc[nt][2 + w] = (p <= pq1 && q1 < T) ? sacc[nt][2 + w] + __ldg(bias_h + (pq1 - p)) : -INFINITY;
+        mx0 = fmaxf(mx0, sacc[nt][w]);
+        mx1 = fmaxf(mx1, sacc[nt][2 + w]);
+      }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    float sum0 = 0.f, sum1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int w = 0; w < 2; ++w) {
+        sacc[nt][w] = mx0 == -INFINITY ? 0.f : expf(sacc[nt][w] - mx0);
+        sacc[nt][2 + w] = mx1 == -INFINITY ? 0.f : expf(sacc[nt][2 + w] - mx1);
+        sum0 += sacc[nt][w];
+        sum1 += sacc[nt][2 + w];
+      }
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+    float oacc[8][4];
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) oacc[nd][u] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks) {
+      uint32_t ph[4], pl[4];
+      bool nb_ = false;
+      split_h2(sacc[2 * ks][0], sacc[2 * ks][1], ph[0], pl[0], nb_);
+      split_h2(sacc[2 * ks][2], sacc[2 * ks][3], ph[1], pl[1], nb_);
+      split_h2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ph[2], pl[2], nb_);
+      split_h2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ph[3], pl[3], nb_);
+#pragma unroll
+      for (int nd = 0; nd < 8; nd += 2) {
+        uint32_t bh[4], bl[4];
+        ldmatrix_x4_trans(bh, v_hi + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
+        ldmatrix_x4_trans(bl, v_lo + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
+        mma_f16(oacc[nd], pl, bh[0], bh[1]);
+        mma_f16(oacc[nd], ph, bl[0], bl[1]);
+        mma_f16(oacc[nd], ph, bh[0], bh[1]);
+        mma_f16(oacc[nd + 1], pl, bh[2], bh[3]);
+        mma_f16(oacc[nd + 1], ph, bl[2], bl[3]);
+        mma_f16(oacc[nd + 1], ph, bh[2], bh[3]);
+      }
+    }
+    const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
+    if (q0 < T) {
+      const int64_t base = ((int64_t)a.lay.off[t + q0] + rp) * inner + h * 64 + 2 * t4;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
+    }
+    if (q1 < T) {
+      const int64_t base = ((int64_t)a.lay.off[t + q1] + rp) * inner + h * 64 + 2 * t4;
+#pragma unroll
+      for (int nd = 0; nd < 8; ++nd)
+        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_v1_kernel(TailAttnArgs a, ActOut ctx) {
   extern __shared__ __align__(16) unsigned char tmsmem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, t4 = lane & 3, half = lane >> 4, l16 = lane & 15;
+  const int half = lane >> 4, l16 = lane & 15;
   __half* k_hi = reinterpret_cast<__half*>(tmsmem + warp * kTailMmaWarpBytes);
   __half* k_lo = k_hi + 32 * kKLd;
   __half* v_hi = k_lo + 32 * kKLd;
   __half* v_lo = v_hi + 32 * kKLd;
-  const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
-  const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
-  const int vrow = (lane & 7) + 8 * ((lane >> 3) & 1), vcol = 8 * (lane >> 4);   // ldmatrix row of this lane
   const int inner = a.H * 64, L = a.L;
   const int P = a.lay.P;
   const int ntask = a.R * a.H;
@@ -916,108 +1027,97 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(Ta
       *reinterpret_cast<uint2*>(v_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
     }
     __syncwarp();
-    // ---- the T queries as 16-row tiles: tile row q = query index (position t + q) --------------------------------
-    for (int tile = 0; tile * 16 < T; ++tile) {
-      const int q0 = tile * 16 + g, q1 = q0 + 8;
-      const float* qr0 = a.qkv + ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
-      const float* qr1 = a.qkv + ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
-      float sacc[4][4];
+    tail_mma16_tiles(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, bad);
+  }
+  if (bad && ctx.overflow) *ctx.overflow = 1;
+  pdl_trigger();
+}
+
+// Same task, software-pipelined: the raw fp32 K/V rows of the NEXT task stream into a staging area with cp.async
+// (16 KB per warp, all of it in flight at once, no registers) while the tensor-core tiles of the current task run;
+// the split into fp16 planes then reads shared memory instead of waiting on HBM. ncu on the version above:
+// long_scoreboard 5.7 of 9 stall cycles per issue, 26 % issue utilisation - the staging latency was the limiter.
+constexpr int kTailRawBytes = 2 * 32 * 64 * 4;                             // raw K | raw V of up to 32 positions
+constexpr int kTailPipeWarpBytes = kTailMmaWarpBytes + kTailRawBytes;      // 34.8 KB per warp -> 6 warps per SM
+constexpr int kTailPipeWarps = 6;
+
+__global__ void __launch_bounds__(kTailPipeWarps * 32, 1) self_attn_tail_mma16_kernel(TailAttnArgs a, ActOut ctx) {
+  extern __shared__ __align__(16) unsigned char tmsmem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int half = lane >> 4, l16 = lane & 15;
+  unsigned char* wbase = tmsmem + warp * kTailPipeWarpBytes;
+  __half* k_hi = reinterpret_cast<__half*>(wbase);
+  __half* k_lo = k_hi + 32 * kKLd;
+  __half* v_hi = k_lo + 32 * kKLd;
+  __half* v_lo = v_hi + 32 * kKLd;
+  float* raw_k = reinterpret_cast<float*>(wbase + kTailMmaWarpBytes);
+  float* raw_v = raw_k + 32 * 64;
+  const int inner = a.H * 64, L = a.L;
+  const int P = a.lay.P;
+  const int ntask = a.R * a.H;
+  const int stride = gridDim.x * kTailPipeWarps;
+  bool bad = false;
+  pdl_wait();
+  // issue the K/V loads of one task into the raw staging area (positions >= P are zero-filled at the split)
+  auto issue = [&](int wid) {
+    const int rp = wid / a.H, h = wid - rp * a.H;
+    const int bq = a.fz_list[rp / a.nb];
+    const int r = bq * a.nb + rp % a.nb;
+    const int t = a.qstart ? a.qstart[bq] : 0;
+    const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) sacc[nt][u] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < 4; ++kk) {
-        const float2 x0 = *reinterpret_cast<const float2*>(qr0 + kk * 16), x1 = *reinterpret_cast<const float2*>(qr1 + kk * 16);
-        const float2 x2 = *reinterpret_cast<const float2*>(qr0 + kk * 16 + 8);
-        const float2 x3 = *reinterpret_cast<const float2*>(qr1 + kk * 16 + 8);
-        uint32_t ah[4], al[4];
-        split_h2(x0.x, x0.y, ah[0], al[0], bad);
-        split_h2(x1.x, x1.y, ah[1], al[1], bad);
-        split_h2(x2.x, x2.y, ah[2], al[2], bad);
-        split_h2(x3.x, x3.y, ah[3], al[3], bad);
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) {
-          const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t4;
-          const uint32_t bh0 = kh32[o0], bh1 = kh32[o0 + 4], bl0 = kl32[o0], bl1 = kl32[o0 + 4];
-          mma_f16(sacc[nt], al, bh0, bh1);
-          mma_f16(sacc[nt], ah, bl0, bl1);
-          mma_f16(sacc[nt], ah, bh0, bh1);
+    for (int it = 0; it < 16; ++it) {
+      const int p = 2 * it + half;
+      const int slot = __shfl_sync(0xffffffffu, slot_l, p);
+      if (p < P) {
+        const float* kp;
+        const float* vp;
+        if (p < t) {
+          kp = a.cache_k + (int64_t)slot * inner + h * 64 + l16 * 4;
+          vp = a.cache_v + (int64_t)slot * inner + h * 64 + l16 * 4;
+        } else {
+          const float* row = a.qkv + ((int64_t)a.lay.off[p] + rp) * 3 * inner + h * 64 + l16 * 4;
+          kp = row + inner;
+          vp = row + 2 * inner;
         }
-      }
-      // causal mask + relative position bias: row q sits at position t + q and sees keys p <= t + q
-      const int pq0 = t + q0, pq1 = t + q1;
-      const float* bias_h = a.bias + h * L;
-      float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          const int p = nt * 8 + 2 * t4 + w;
-          sacc[nt][w] = (p <= pq0 && q0 < T) ? sacc[nt][w] + __ldg(bias_h + (pq0 - p)) : -INFINITY;
-          sacc[nt][2 + w] = (p <= pq1 && q1 < T) ? sacc[nt][2 + w] + __ldg(bias_h + (pq1 - p)) : -INFINITY;
-          mx0 = fmaxf(mx0, sacc[nt][w]);
-          mx1 = fmaxf(mx1, sacc[nt][2 + w]);
-        }
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      float sum0 = 0.f, sum1 = 0.f;
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int w = 0; w < 2; ++w) {
-          sacc[nt][w] = mx0 == -INFINITY ? 0.f : expf(sacc[nt][w] - mx0);
-          sacc[nt][2 + w] = mx1 == -INFINITY ? 0.f : expf(sacc[nt][2 + w] - mx1);
-          sum0 += sacc[nt][w];
-          sum1 += sacc[nt][2 + w];
-        }
-      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-      sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-      sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-      float oacc[8][4];
-#pragma unroll
-      for (int nd = 0; nd < 8; ++nd)
-#pragma unroll
-        for (int u = 0; u < 4; ++u) oacc[nd][u] = 0.f;
-#pragma unroll
-      for (int ks = 0; ks < 2; ++ks) {
-        uint32_t ph[4], pl[4];
-        bool nb_ = false;
-        split_h2(sacc[2 * ks][0], sacc[2 * ks][1], ph[0], pl[0], nb_);
-        split_h2(sacc[2 * ks][2], sacc[2 * ks][3], ph[1], pl[1], nb_);
-        split_h2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ph[2], pl[2], nb_);
-        split_h2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ph[3], pl[3], nb_);
-#pragma unroll
-        for (int nd = 0; nd < 8; nd += 2) {
-          uint32_t bh[4], bl[4];
-          ldmatrix_x4_trans(bh, v_hi + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
-          ldmatrix_x4_trans(bl, v_lo + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
-          mma_f16(oacc[nd], pl, bh[0], bh[1]);
-          mma_f16(oacc[nd], ph, bl[0], bl[1]);
-          mma_f16(oacc[nd], ph, bh[0], bh[1]);
-          mma_f16(oacc[nd + 1], pl, bh[2], bh[3]);
-          mma_f16(oacc[nd + 1], ph, bl[2], bl[3]);
-          mma_f16(oacc[nd + 1], ph, bh[2], bh[3]);
-        }
-      }
-      const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
-      if (q0 < T) {
-        const int64_t base = ((int64_t)a.lay.off[t + q0] + rp) * inner + h * 64 + 2 * t4;
-#pragma unroll
-        for (int nd = 0; nd < 8; ++nd)
-          act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
-      }
-      if (q1 < T) {
-        const int64_t base = ((int64_t)a.lay.off[t + q1] + rp) * inner + h * 64 + 2 * t4;
-#pragma unroll
-        for (int nd = 0; nd < 8; ++nd)
-          act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
+        cp_async16_on(raw_k + p * 64 + l16 * 4, kp);
+        cp_async16_on(raw_v + p * 64 + l16 * 4, vp);
       }
     }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int wid = blockIdx.x * kTailPipeWarps + warp;
+  if (wid < ntask) issue(wid);
+  for (; wid < ntask; wid += stride) {
+    const int rp = wid / a.H, h = wid - rp * a.H;                   // frozen row (freeze order), head
+    const int bq = a.fz_list[rp / a.nb];
+    const int t = a.qstart ? a.qstart[bq] : 0, T = P - t;           // this row's pass: positions t..P-1
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();                                                   // raw rows landed; the previous task's tiles are done
+    // ---- split the staged rows into fp16 planes (rows >= P: zeros) ------------------------------------------------
+#pragma unroll 4
+    for (int it = 0; it < 16; ++it) {
+      const int p = 2 * it + half;
+      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
+      if (p < P) {
+        kk = *reinterpret_cast<const float4*>(raw_k + p * 64 + l16 * 4);
+        vv = *reinterpret_cast<const float4*>(raw_v + p * 64 + l16 * 4);
+      }
+      uint32_t h0, l0, h1, l1;
+      split_h2(kk.x, kk.y, h0, l0, bad);
+      split_h2(kk.z, kk.w, h1, l1, bad);
+      *reinterpret_cast<uint2*>(k_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(k_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
+      split_h2(vv.x, vv.y, h0, l0, bad);
+      split_h2(vv.z, vv.w, h1, l1, bad);
+      *reinterpret_cast<uint2*>(v_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
+      *reinterpret_cast<uint2*>(v_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
+    }
+    __syncwarp();                                                   // planes complete, raw area free again
+    if (wid + stride < ntask) issue(wid + stride);                  // next task's rows fly while this one computes
+    tail_mma16_tiles(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, bad);
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (bad && ctx.overflow) *ctx.overflow = 1;
   pdl_trigger();
 }
@@ -1094,24 +1194,34 @@ int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s) {
     return !(e && e[0] == '0');
   }();
   const bool mma = use_mma && prec_is_fp16(ctx.mode);      // tensor-core kernel on fp16 planes; FFMA kernel otherwise
-  const size_t smem = mma ? (size_t)kWarps * kTailMmaWarpBytes : (size_t)kWarps * kTailWarpFloats * sizeof(float);
+  const char* ve = getenv("RB200_SELF_TAIL");              // v1: the unpipelined tensor-core kernel (A/B measurements)
+  const bool v1 = ve && strcmp(ve, "v1") == 0;
   static bool attr_set = false;
   static int sms = 0;
   if (!attr_set) {
     RB_CUDA(cudaFuncSetAttribute(self_attn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)kWarps * kTailWarpFloats * sizeof(float))));
-    RB_CUDA(cudaFuncSetAttribute(self_attn_tail_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    RB_CUDA(cudaFuncSetAttribute(self_attn_tail_mma16_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)kWarps * kTailMmaWarpBytes)));
+    RB_CUDA(cudaFuncSetAttribute(self_attn_tail_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 kTailPipeWarps * kTailPipeWarpBytes));
     int dev = 0;
     RB_CUDA(cudaGetDevice(&dev));
     RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
-  const int want = ceil_div((int64_t)a.R * a.H, kWarps);
-  const int per_sm = mma ? 3 : 2;
-  const dim3 grid(want < per_sm * sms ? want : per_sm * sms), block(kWarps * 32);
-  if (mma) RB_CUDA(launch_pdl(self_attn_tail_mma16_kernel, grid, block, smem, s, a, ctx));
-  else RB_CUDA(launch_pdl(self_attn_tail_kernel, grid, block, smem, s, a, ctx));
+  if (mma && !v1) {
+    const int want = ceil_div((int64_t)a.R * a.H, kTailPipeWarps);
+    const dim3 grid(want < sms ? want : sms), block(kTailPipeWarps * 32);
+    RB_CUDA(launch_pdl(self_attn_tail_mma16_kernel, grid, block, (size_t)kTailPipeWarps * kTailPipeWarpBytes, s, a, ctx));
+  } else {
+    const size_t smem = mma ? (size_t)kWarps * kTailMmaWarpBytes : (size_t)kWarps * kTailWarpFloats * sizeof(float);
+    const int want = ceil_div((int64_t)a.R * a.H, kWarps);
+    const int per_sm = mma ? 3 : 2;
+    const dim3 grid(want < per_sm * sms ? want : per_sm * sms), block(kWarps * 32);
+    if (mma) RB_CUDA(launch_pdl(self_attn_tail_mma16_v1_kernel, grid, block, smem, s, a, ctx));
+    else RB_CUDA(launch_pdl(self_attn_tail_kernel, grid, block, smem, s, a, ctx));
+  }
   launch_count()++;
   return 0;
 }

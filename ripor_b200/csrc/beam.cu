@@ -31,6 +31,9 @@ namespace {
 
 constexpr int kMaxPerThread = 128;   // candidates owned by one thread of the arg-max kernel (128-bit taken mask)
 constexpr double kNanRank = -1.7976931348623157e308;   // a NaN candidate ranks last, by index
+// A query may be frozen only when every beam sits on a single leaf AND none carries the -1e9 penalty: only then is it
+// certain that the beams' single valid children outrank every penalised candidate at each remaining step.
+constexpr double kPenalised = -1e8;
 
 __device__ __forceinline__ bool cand_better(double va, int ia, double vb, int ib) {
   return va > vb || (va == vb && ia < ib);
@@ -119,7 +122,7 @@ __device__ __forceinline__ void cta_write_back(const StepArgs& a, int b, const d
       ns = s.node >= 0 ? child_explicit_warp(a.tv, s, v, lane) : child_implicit_warp(a.tv, s, t, v, lane);
     if (lane == 0) {
       ns_s[j] = ns;
-      if (ns.hi - ns.lo == 1) atomicAdd(n_single, 1);
+      if (ns.hi - ns.lo == 1 && win_val[j] > kPenalised) atomicAdd(n_single, 1);
     }
   }
   __syncthreads();
@@ -633,7 +636,8 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
     }
   }
   // every beam on a single leaf: the rest of the query's DocIDs is determined by the trie -> freeze it
-  const bool frozen = a.allow_freeze && __all_sync(0xffffffffu, lane >= nb || ns.hi - ns.lo == 1);
+  const bool frozen = a.allow_freeze &&
+                      __all_sync(0xffffffffu, lane >= nb || (ns.hi - ns.lo == 1 && win_val[lane] > kPenalised));
   double* sc_out = frozen ? a.sc_fz : a.sc_new;
   TrieState* st_out = frozen ? a.st_fz : a.st_new;
   int32_t* hist_out = frozen ? a.hist_fz : a.hist_new;

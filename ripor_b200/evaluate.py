@@ -194,6 +194,29 @@ def _docids_of(trie: DocidTrie, docs, counts, leaf, q: int, j: int) -> List[str]
     return trie.docids_for_range(lo, hi)
 
 
+def retrieve_batch(model, prefix_constrain_processor, input_ids, attention_mask, max_new_token: int, topk: int,
+                   apply_log_softmax_for_scores: bool = False, width: int = LEAF_EXPAND_WIDTH, precision=None):
+    """One batch through the whole path, host to host: pinned (or pageable) ``input_ids`` / ``attention_mask`` [B, S]
+    are copied to the model's device, searched, the ranked DocIDs expanded to documents on the device
+    (evaluate.py:118-128) and the result copied back. Returns host tensors (doc rows int64 [B, topk, width] in json
+    order padded with -1, document counts int32 [B, topk], scores fp32 [B, topk], leaf ranges int32 [B, topk, 2]) and
+    the generate output. This is the body of ``constrained_decode_doc``'s loop and what bench.py times as ``e2e``."""
+    dev = model.device if hasattr(model, "device") else torch.device("cuda", torch.cuda.current_device())
+    ids = input_ids.to(dev, non_blocking=True).long()
+    mask = attention_mask.to(dev, non_blocking=True).long()
+    out = generate_for_constrained_prefix_beam_search(
+        model, prefix_constrain_processor, input_ids=ids, attention_mask=mask, max_new_tokens=max_new_token,
+        output_scores=True, return_dict=True, return_dict_in_generate=True, num_beams=topk, num_return_sequences=topk,
+        apply_log_softmax_for_scores=apply_log_softmax_for_scores, precision=precision)
+    docs, counts = prefix_constrain_processor.trie.expand_ranges(out.leaf_ranges, width)
+    B = ids.shape[0]
+    res = (docs.view(B, topk, width).to("cpu", non_blocking=True), counts.view(B, topk).to("cpu", non_blocking=True),
+           out.sequences_scores.view(B, topk).to("cpu", non_blocking=True),
+           out.leaf_ranges.view(B, topk, 2).to("cpu", non_blocking=True))
+    torch.cuda.current_stream(dev).synchronize()
+    return res, out
+
+
 def constrained_decode_doc(model, dataloader, prefix_constrain_processor, smtid_to_docids, max_new_token, device,
                            out_dir, local_rank, topk=100, apply_log_softmax_for_scores=False, write=True):
     """smtid_to_docids: the reference's dict {"c1_.._cL": [docids]} or None to expand leaves from the trie."""
@@ -407,9 +430,9 @@ def gather_runs(local_run: Dict, group=None) -> Optional[Dict]:
     order = ("qids", "lens", "off", "scores", "names")
     blobs = [np.ascontiguousarray(p[k]).view(np.uint8).reshape(-1) for k in order]
     sizes = torch.tensor([b.size for b in blobs], dtype=torch.int64, device=dev)
-    all_sizes = torch.zeros((world, len(order)), dtype=torch.int64, device=dev)
+    all_sizes = torch.zeros(world * len(order), dtype=torch.int64, device=dev)
     dist.all_gather_into_tensor(all_sizes, sizes, group=group)
-    all_sizes = all_sizes.cpu().numpy()
+    all_sizes = all_sizes.cpu().numpy().reshape(world, len(order))
     cap = int(all_sizes.sum(axis=1).max())
     cap = (cap + 15) // 16 * 16
     payload = torch.zeros(cap, dtype=torch.uint8, device=dev)
@@ -433,24 +456,25 @@ def gather_runs(local_run: Dict, group=None) -> Optional[Dict]:
 
 def gather_ranked_lists(qids: torch.Tensor, doc_rows: torch.Tensor, scores: torch.Tensor, group=None):
     """The per-batch collective of the data path: all_gather of the packed ranked lists
-    ``doc_rows`` int64 [B_loc, nb] (+ ``scores`` fp32 [B_loc, nb], ``qids`` int64 [B_loc]) over NCCL. Every rank gets
-    ([world*B_loc], [world*B_loc, nb], [world*B_loc, nb]); rows of padded (duplicated) queries are dropped by the
-    caller with ``unique_queries``. Without a process group the inputs are returned."""
+    ``doc_rows`` int64 [B_loc, m] (+ ``scores`` fp32 [B_loc, n], ``qids`` int64 [B_loc]) over NCCL. Every rank gets
+    ([world*B_loc], [world*B_loc, m], [world*B_loc, n]) in global query order; rows of padded (duplicated) queries
+    are dropped by the caller with ``unique_queries``. Without a process group the inputs are returned."""
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
         return qids, doc_rows, scores
     world = dist.get_world_size(group)
-    B, nb = doc_rows.shape
+    B, m = doc_rows.shape
+    n = scores.shape[1]
     # one packed int64 buffer per rank: [qid | doc rows | score bits]
-    packed = torch.empty((B, 1 + 2 * nb), dtype=torch.int64, device=doc_rows.device)
+    packed = torch.empty((B, 1 + m + n), dtype=torch.int64, device=doc_rows.device)
     packed[:, 0] = qids.to(doc_rows.device)
-    packed[:, 1: 1 + nb] = doc_rows
-    packed[:, 1 + nb:] = scores.to(torch.float32).contiguous().view(torch.int32).to(torch.int64)
-    out = torch.empty((world * B, 1 + 2 * nb), dtype=torch.int64, device=doc_rows.device)
+    packed[:, 1: 1 + m] = doc_rows
+    packed[:, 1 + m:] = scores.to(torch.float32).contiguous().view(torch.int32).to(torch.int64)
+    out = torch.empty((world * B, 1 + m + n), dtype=torch.int64, device=doc_rows.device)
     dist.all_gather_into_tensor(out, packed, group=group)
     # DistributedSampler order: global index i*world + rank  <->  row rank*B + i
     out = out.view(world, B, -1).transpose(0, 1).reshape(world * B, -1)
-    return out[:, 0], out[:, 1: 1 + nb], out[:, 1 + nb:].to(torch.int32).view(torch.float32)
+    return out[:, 0], out[:, 1: 1 + m], out[:, 1 + m:].to(torch.int32).view(torch.float32)
 
 
 def unique_queries(qids: torch.Tensor, n_queries: int) -> torch.Tensor:

@@ -195,7 +195,7 @@ class T5ForDocIDGeneration:
         # Source lengths come in buckets of 32 positions (the loader pads every batch to its own longest row,
         # dataloader.py:62-79), and an engine serves every batch <= max_batch, num_beams <= max_beams, S <= max_src_len.
         # When a call does not fit, only the workspaces are re-allocated (the packed weights stay): to the union of the
-        # old and new shapes if that is not much bigger than either, else to the new shape.
+        # old and new shapes if that costs at most 25 % more rows than the larger of the two, else to the new shape.
         src_cap = _round_up(max(src_len, 8), 32)
         e = self._engines.get(precision)
         if e is not None and e.key[0] != dev:
@@ -211,7 +211,7 @@ class T5ForDocIDGeneration:
             return e
         union = (max(mb, batch), max(nb, num_beams), max(ms, src_cap))
         exact = (batch, num_beams, max(ms, src_cap))
-        new = union if union[0] * union[1] <= 2 * max(mb * nb, batch * num_beams) else exact
+        new = union if union[0] * union[1] <= 1.25 * max(mb * nb, batch * num_beams) else exact
         with torch.cuda.device(dev):
             torch.cuda.synchronize()
             e.resize(*new)

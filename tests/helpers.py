@@ -56,3 +56,32 @@ def compare_ranked(seqs, scores, ref_seqs, ref_scores, nb, atol=1e-3, near_tie=0
     assert torch.allclose(scores[valid & ~mism], ref_scores[valid & ~mism], atol=atol, rtol=0), \
         f"score diff {(scores - ref_scores)[valid & ~mism].abs().max()}"
     return int(mism.view(-1, nb).any(dim=1).sum())
+
+
+def compare_ranked_near_tie(seqs, scores, ref_seqs, ref_scores, nb, trace, eps=2e-4, atol=1e-3):
+    """Like compare_ranked, but separates NEAR-TIES from real mismatches (hard part 1): a query whose oracle
+    run had, at some step, less than ``eps`` between the last candidate kept in the beam and the first one dropped can
+    legitimately keep the other candidate under any fp32-grade arithmetic (the observed score noise is ~2e-5). For
+    such a query the ranked lists must still agree on all but a handful of rows and on the scores of the rows they
+    share. Returns (queries that really differ, queries that differ within a near-tie)."""
+    seqs, ref_seqs = seqs.cpu(), ref_seqs.cpu()
+    scores, ref_scores = scores.cpu().double(), ref_scores.cpu().double()
+    B = seqs.shape[0] // nb
+    min_gap = torch.stack([t["cut_gap"] for t in trace], 0).min(0).values          # [B]
+    real = near = 0
+    for b in range(B):
+        sl = slice(b * nb, (b + 1) * nb)
+        if torch.equal(seqs[sl], ref_seqs[sl]):
+            assert torch.allclose(scores[sl], ref_scores[sl], atol=atol, rtol=0)
+            continue
+        got = {tuple(r): float(s) for r, s in zip(seqs[sl].tolist(), scores[sl])}
+        ref = {tuple(r): float(s) for r, s in zip(ref_seqs[sl].tolist(), ref_scores[sl])}
+        common = set(got) & set(ref)
+        order_only = len(common) == nb                               # same rows, two neighbours swapped places
+        ok = all(abs(got[k] - ref[k]) <= atol for k in common) and len(common) >= nb - max(4, nb // 100)
+        if ok and (order_only or float(min_gap[b]) < eps):
+            near += 1
+        else:
+            real += 1
+    return real, near
+

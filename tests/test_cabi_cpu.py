@@ -122,3 +122,39 @@ def test_new_entry_points_validate_arguments_without_a_gpu():
     assert L.rb200_gemm_bench(5, 0, 128, 64, 0, 1, 0, C.byref(us), None) != 0        # empty problem
     assert b"precision" in L.rb200_last_error() or b"bad argument" in L.rb200_last_error()
     assert L.rb200_engine_last_tail_step(None) == -1
+
+
+def test_round2_entry_points_validate_arguments_without_a_gpu():
+    """The entry points added in round 2 answer bad arguments with a status and a message, never a crash."""
+    import ctypes as C
+    import numpy as np
+    L = _lib.lib()
+    codes = syn.make_codes(50, 4, 8, seed=1)
+    tr = DocidTrie.from_codes(codes, 8)
+    ranges = np.zeros((2, 2), np.int32)
+    docs, counts = np.zeros((2, 4), np.int64), np.zeros(2, np.int32)
+    # leaf expansion needs an uploaded trie and a sane width
+    assert L.rb200_trie_leaf_expand(tr.handle, ranges.ctypes.data, 2, 4, docs.ctypes.data, counts.ctypes.data, None) == -4
+    assert b"not uploaded" in L.rb200_last_error()
+    assert L.rb200_trie_leaf_expand(tr.handle, ranges.ctypes.data, 2, 0, docs.ctypes.data, counts.ctypes.data, None) == -1
+    assert L.rb200_trie_leaf_expand(None, None, 0, 4, None, None, None) == -1
+    # engine entry points with null handles
+    assert L.rb200_engine_resize(None, 1, 1, 1) == -1
+    assert L.rb200_engine_forward(None, None, None, 1, 1, 1, None, 1, None, None, None, None) == -1
+    assert L.rb200_engine_last_freeze_histogram(None, None, 0, None) == -1
+    nx = C.c_void_p()
+    assert L.rb200_engine_next_input(None, C.byref(nx)) == -1
+    assert L.rb200_beam_forced_tail(None, None, 1, None, 0, None) == -1
+    assert L.rb200_beam_reset_beams(None, None, 1, 1, None) == -1
+    # readers
+    tab = C.c_void_p()
+    assert L.rb200_docid_json_open(b"/nonexistent/docid_to_smtid.json", 0, C.byref(tab)) == -3
+    assert L.rb200_docid_json_open(None, 0, C.byref(tab)) == -1
+    assert L.rb200_unpack_codes(None, 1, 1, 1, 8, None) == -1
+    out = np.zeros(4, np.int32)
+    packed = np.zeros(4, np.uint8)
+    assert L.rb200_unpack_codes(packed.ctypes.data, 1, 4, 4, 30, out.ctypes.data) == -1       # bits > 24
+    # a beam wider than the select kernel's shared-memory budget is refused at creation, with a message
+    h = C.c_void_p()
+    assert L.rb200_beam_create(0, 1, 4096, 4, 256, C.byref(h)) == -1
+    assert b"exceeds the beam kernels" in L.rb200_last_error()
