@@ -759,13 +759,28 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
     const int q0 = tile * 16 + g, q1 = q0 + 8;
     const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64 + 2 * t;
     const float* qr1 = a.q + global_row(min(q1, nrows - 1)) * q_ld + h * 64 + 2 * t;
+    const bool qplanes = a.q_hi != nullptr;                         // q arrives as fp16 hi/lo planes (EPI_PLANES)
+    const __half* qh0 = a.q_hi + global_row(min(q0, nrows - 1)) * q_ld + h * 64 + 2 * t;
+    const __half* qh1 = a.q_hi + global_row(min(q1, nrows - 1)) * q_ld + h * 64 + 2 * t;
     float2 qa[4][4];                                                // A fragments (raw fp32 pairs) of the 4 k-steps
+    uint32_t qph[4][4], qpl[4][4];                                  // ... or the plane words as they are
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      qa[kk][0] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16));
-      qa[kk][1] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16));
-      qa[kk][2] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16 + 8));
-      qa[kk][3] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16 + 8));
+      if (qplanes) {
+        qph[kk][0] = __ldg(reinterpret_cast<const uint32_t*>(qh0 + kk * 16));
+        qph[kk][1] = __ldg(reinterpret_cast<const uint32_t*>(qh1 + kk * 16));
+        qph[kk][2] = __ldg(reinterpret_cast<const uint32_t*>(qh0 + kk * 16 + 8));
+        qph[kk][3] = __ldg(reinterpret_cast<const uint32_t*>(qh1 + kk * 16 + 8));
+        qpl[kk][0] = __ldg(reinterpret_cast<const uint32_t*>(qh0 + a.q_plane + kk * 16));
+        qpl[kk][1] = __ldg(reinterpret_cast<const uint32_t*>(qh1 + a.q_plane + kk * 16));
+        qpl[kk][2] = __ldg(reinterpret_cast<const uint32_t*>(qh0 + a.q_plane + kk * 16 + 8));
+        qpl[kk][3] = __ldg(reinterpret_cast<const uint32_t*>(qh1 + a.q_plane + kk * 16 + 8));
+      } else {
+        qa[kk][0] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16));
+        qa[kk][1] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16));
+        qa[kk][2] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16 + 8));
+        qa[kk][3] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16 + 8));
+      }
     }
     float sacc[4][4];
 #pragma unroll
@@ -776,7 +791,10 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
     for (int kk = 0; kk < 4; ++kk) {
       uint32_t ah[4], al[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) split_h2(qa[kk][u].x, qa[kk][u].y, ah[u], al[u], bad);
+      for (int u = 0; u < 4; ++u) {
+        if (qplanes) { ah[u] = qph[kk][u]; al[u] = qpl[kk][u]; }
+        else split_h2(qa[kk][u].x, qa[kk][u].y, ah[u], al[u], bad);
+      }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t;      // words: K[key nt*8+g][dims kk*16 + 2t, +1]
@@ -871,6 +889,7 @@ constexpr int kTailMmaWarpBytes = 4 * 32 * kKLd * 2;          // K hi | K lo | V
 __device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const ActOut& ctx, const __half* k_hi,
                                                  const __half* k_lo, const __half* v_hi, const __half* v_lo, int rp,
                                                  int h, int t, int T, bool& bad) {
+  const bool qplanes = a.qkv_hi != nullptr;    // q | k | v arrive as fp16 hi/lo planes (EPI_PLANES): no split here
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
@@ -880,8 +899,12 @@ __device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const Ac
   // ---- the T queries as 16-row tiles: tile row q = query index (position t + q) --------------------------------
   for (int tile = 0; tile * 16 < T; ++tile) {
     const int q0 = tile * 16 + g, q1 = q0 + 8;
-    const float* qr0 = a.qkv + ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
-    const float* qr1 = a.qkv + ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+    const int64_t qo0 = ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+    const int64_t qo1 = ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+    const float* qr0 = a.qkv + qo0;
+    const float* qr1 = a.qkv + qo1;
+    const __half* qh0 = a.qkv_hi + qo0;
+    const __half* qh1 = a.qkv_hi + qo1;
     float sacc[4][4];
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -889,14 +912,25 @@ __device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const Ac
       for (int u = 0; u < 4; ++u) sacc[nt][u] = 0.f;
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const float2 x0 = *reinterpret_cast<const float2*>(qr0 + kk * 16), x1 = *reinterpret_cast<const float2*>(qr1 + kk * 16);
-      const float2 x2 = *reinterpret_cast<const float2*>(qr0 + kk * 16 + 8);
-      const float2 x3 = *reinterpret_cast<const float2*>(qr1 + kk * 16 + 8);
       uint32_t ah[4], al[4];
-      split_h2(x0.x, x0.y, ah[0], al[0], bad);
-      split_h2(x1.x, x1.y, ah[1], al[1], bad);
-      split_h2(x2.x, x2.y, ah[2], al[2], bad);
-      split_h2(x3.x, x3.y, ah[3], al[3], bad);
+      if (qplanes) {
+        ah[0] = *reinterpret_cast<const uint32_t*>(qh0 + kk * 16);
+        ah[1] = *reinterpret_cast<const uint32_t*>(qh1 + kk * 16);
+        ah[2] = *reinterpret_cast<const uint32_t*>(qh0 + kk * 16 + 8);
+        ah[3] = *reinterpret_cast<const uint32_t*>(qh1 + kk * 16 + 8);
+        al[0] = *reinterpret_cast<const uint32_t*>(qh0 + a.qkv_plane + kk * 16);
+        al[1] = *reinterpret_cast<const uint32_t*>(qh1 + a.qkv_plane + kk * 16);
+        al[2] = *reinterpret_cast<const uint32_t*>(qh0 + a.qkv_plane + kk * 16 + 8);
+        al[3] = *reinterpret_cast<const uint32_t*>(qh1 + a.qkv_plane + kk * 16 + 8);
+      } else {
+        const float2 x0 = *reinterpret_cast<const float2*>(qr0 + kk * 16), x1 = *reinterpret_cast<const float2*>(qr1 + kk * 16);
+        const float2 x2 = *reinterpret_cast<const float2*>(qr0 + kk * 16 + 8);
+        const float2 x3 = *reinterpret_cast<const float2*>(qr1 + kk * 16 + 8);
+        split_h2(x0.x, x0.y, ah[0], al[0], bad);
+        split_h2(x1.x, x1.y, ah[1], al[1], bad);
+        split_h2(x2.x, x2.y, ah[2], al[2], bad);
+        split_h2(x3.x, x3.y, ah[3], al[3], bad);
+      }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t4;
@@ -980,7 +1014,17 @@ __device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const Ac
   }
 }
 
-__global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_v1_kernel(TailAttnArgs a, ActOut ctx) {
+__device__ __forceinline__ void cp_async16_any(void* dst_smem, const void* src) {
+  const uint32_t d32 = (uint32_t)__cvta_generic_to_shared(dst_smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src) : "memory");
+}
+
+// ncu on the round-1 version of this kernel (everything staged from fp32 and split here): 4200 warp instructions per
+// task, ~60 % of them the fp32 -> fp16 hi/lo split of K, V and Q; 28 % issue utilisation at 12 warps per SM. With the
+// qkv GEMM of the pass writing fp16 hi/lo planes (EPI_PLANES) the rows of the pass are copied plane-to-plane with
+// cp.async (one 16-byte chunk per lane and position: 4 planes x 8 chunks) and only the few cached positions (< t)
+// are still split here; Q fragments are read from the planes as they are.
+__global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(TailAttnArgs a, ActOut ctx) {
   extern __shared__ __align__(16) unsigned char tmsmem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;
@@ -991,7 +1035,20 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_v1_kernel
   const int inner = a.H * 64, L = a.L;
   const int P = a.lay.P;
   const int ntask = a.R * a.H;
+  const bool planes = a.qkv_hi != nullptr;
   bool bad = false;
+  // rows >= P are never written by a task: zero them once (their scores are masked, but 0 * garbage must not happen)
+  for (int e = lane; e < (32 - P) * 8; e += 32) {
+    const int p = P + (e >> 3), ch = e & 7;
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(k_hi + p * kKLd + ch * 8) = z;
+    *reinterpret_cast<uint4*>(k_lo + p * kKLd + ch * 8) = z;
+    *reinterpret_cast<uint4*>(v_hi + p * kKLd + ch * 8) = z;
+    *reinterpret_cast<uint4*>(v_lo + p * kKLd + ch * 8) = z;
+  }
+  // plane copy: lane -> (plane, 16-byte chunk of the 64-dim head row)
+  const int pl = lane >> 3, ch = lane & 7;
+  __half* dst_plane = (pl == 0 ? k_hi : (pl == 1 ? k_lo : (pl == 2 ? v_hi : v_lo))) + ch * 8;
   pdl_wait();
   for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += gridDim.x * kWarps) {
     const int rp = wid / a.H, h = wid - rp * a.H;                   // frozen row (freeze order), head
@@ -999,14 +1056,22 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_v1_kernel
     const int r = bq * a.nb + rp % a.nb;                            // original row id
     const int t = a.qstart ? a.qstart[bq] : 0, T = P - t;           // this row's pass: positions t..P-1
     __syncwarp();                                                   // the previous task's fragment reads are done
-    // ---- stage and split K, V of positions 0..P-1 (rows >= P: zeros) -------------------------------------------
+    if (planes) {
+      const __half* src = a.qkv_hi + ((pl & 1) ? a.qkv_plane : 0) + ((pl >> 1) ? 2 * inner : inner) + h * 64 + ch * 8;
+      for (int p = t; p < P; ++p)
+        cp_async16_any(dst_plane + p * kKLd, src + ((int64_t)a.lay.off[p] + rp) * 3 * inner);
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    // ---- positions that arrive as fp32 (the cached prefix; everything when there are no planes): split here -------
+    const int nconv = planes ? t : P;
     const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
 #pragma unroll 4
     for (int it = 0; it < 16; ++it) {
+      if (2 * it >= nconv) break;                                   // warp-uniform
       const int p = 2 * it + half;
       const int slot = __shfl_sync(0xffffffffu, slot_l, p);
-      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
-      if (p < P) {
+      if (p < nconv) {
+        float4 kk, vv;
         if (p < t) {
           kk = *reinterpret_cast<const float4*>(a.cache_k + (int64_t)slot * inner + h * 64 + l16 * 4);
           vv = *reinterpret_cast<const float4*>(a.cache_v + (int64_t)slot * inner + h * 64 + l16 * 4);
@@ -1015,109 +1080,21 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_v1_kernel
           kk = *reinterpret_cast<const float4*>(row + inner);
           vv = *reinterpret_cast<const float4*>(row + 2 * inner);
         }
+        uint32_t h0, l0, h1, l1;
+        split_h2(kk.x, kk.y, h0, l0, bad);
+        split_h2(kk.z, kk.w, h1, l1, bad);
+        *reinterpret_cast<uint2*>(k_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(k_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
+        split_h2(vv.x, vv.y, h0, l0, bad);
+        split_h2(vv.z, vv.w, h1, l1, bad);
+        *reinterpret_cast<uint2*>(v_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(v_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
       }
-      uint32_t h0, l0, h1, l1;
-      split_h2(kk.x, kk.y, h0, l0, bad);
-      split_h2(kk.z, kk.w, h1, l1, bad);
-      *reinterpret_cast<uint2*>(k_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(k_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
-      split_h2(vv.x, vv.y, h0, l0, bad);
-      split_h2(vv.z, vv.w, h1, l1, bad);
-      *reinterpret_cast<uint2*>(v_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(v_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
     }
+    if (planes) asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncwarp();
     tail_mma16_tiles(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, bad);
   }
-  if (bad && ctx.overflow) *ctx.overflow = 1;
-  pdl_trigger();
-}
-
-// Same task, software-pipelined: the raw fp32 K/V rows of the NEXT task stream into a staging area with cp.async
-// (16 KB per warp, all of it in flight at once, no registers) while the tensor-core tiles of the current task run;
-// the split into fp16 planes then reads shared memory instead of waiting on HBM. ncu on the version above:
-// long_scoreboard 5.7 of 9 stall cycles per issue, 26 % issue utilisation - the staging latency was the limiter.
-constexpr int kTailRawBytes = 2 * 32 * 64 * 4;                             // raw K | raw V of up to 32 positions
-constexpr int kTailPipeWarpBytes = kTailMmaWarpBytes + kTailRawBytes;      // 34.8 KB per warp -> 6 warps per SM
-constexpr int kTailPipeWarps = 6;
-
-__global__ void __launch_bounds__(kTailPipeWarps * 32, 1) self_attn_tail_mma16_kernel(TailAttnArgs a, ActOut ctx) {
-  extern __shared__ __align__(16) unsigned char tmsmem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int half = lane >> 4, l16 = lane & 15;
-  unsigned char* wbase = tmsmem + warp * kTailPipeWarpBytes;
-  __half* k_hi = reinterpret_cast<__half*>(wbase);
-  __half* k_lo = k_hi + 32 * kKLd;
-  __half* v_hi = k_lo + 32 * kKLd;
-  __half* v_lo = v_hi + 32 * kKLd;
-  float* raw_k = reinterpret_cast<float*>(wbase + kTailMmaWarpBytes);
-  float* raw_v = raw_k + 32 * 64;
-  const int inner = a.H * 64, L = a.L;
-  const int P = a.lay.P;
-  const int ntask = a.R * a.H;
-  const int stride = gridDim.x * kTailPipeWarps;
-  bool bad = false;
-  pdl_wait();
-  // issue the K/V loads of one task into the raw staging area (positions >= P are zero-filled at the split)
-  auto issue = [&](int wid) {
-    const int rp = wid / a.H, h = wid - rp * a.H;
-    const int bq = a.fz_list[rp / a.nb];
-    const int r = bq * a.nb + rp % a.nb;
-    const int t = a.qstart ? a.qstart[bq] : 0;
-    const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
-#pragma unroll
-    for (int it = 0; it < 16; ++it) {
-      const int p = 2 * it + half;
-      const int slot = __shfl_sync(0xffffffffu, slot_l, p);
-      if (p < P) {
-        const float* kp;
-        const float* vp;
-        if (p < t) {
-          kp = a.cache_k + (int64_t)slot * inner + h * 64 + l16 * 4;
-          vp = a.cache_v + (int64_t)slot * inner + h * 64 + l16 * 4;
-        } else {
-          const float* row = a.qkv + ((int64_t)a.lay.off[p] + rp) * 3 * inner + h * 64 + l16 * 4;
-          kp = row + inner;
-          vp = row + 2 * inner;
-        }
-        cp_async16_on(raw_k + p * 64 + l16 * 4, kp);
-        cp_async16_on(raw_v + p * 64 + l16 * 4, vp);
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  };
-  int wid = blockIdx.x * kTailPipeWarps + warp;
-  if (wid < ntask) issue(wid);
-  for (; wid < ntask; wid += stride) {
-    const int rp = wid / a.H, h = wid - rp * a.H;                   // frozen row (freeze order), head
-    const int bq = a.fz_list[rp / a.nb];
-    const int t = a.qstart ? a.qstart[bq] : 0, T = P - t;           // this row's pass: positions t..P-1
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncwarp();                                                   // raw rows landed; the previous task's tiles are done
-    // ---- split the staged rows into fp16 planes (rows >= P: zeros) ------------------------------------------------
-#pragma unroll 4
-    for (int it = 0; it < 16; ++it) {
-      const int p = 2 * it + half;
-      float4 kk = make_float4(0.f, 0.f, 0.f, 0.f), vv = kk;
-      if (p < P) {
-        kk = *reinterpret_cast<const float4*>(raw_k + p * 64 + l16 * 4);
-        vv = *reinterpret_cast<const float4*>(raw_v + p * 64 + l16 * 4);
-      }
-      uint32_t h0, l0, h1, l1;
-      split_h2(kk.x, kk.y, h0, l0, bad);
-      split_h2(kk.z, kk.w, h1, l1, bad);
-      *reinterpret_cast<uint2*>(k_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(k_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
-      split_h2(vv.x, vv.y, h0, l0, bad);
-      split_h2(vv.z, vv.w, h1, l1, bad);
-      *reinterpret_cast<uint2*>(v_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
-      *reinterpret_cast<uint2*>(v_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
-    }
-    __syncwarp();                                                   // planes complete, raw area free again
-    if (wid + stride < ntask) issue(wid + stride);                  // next task's rows fly while this one computes
-    tail_mma16_tiles(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, bad);
-  }
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
   if (bad && ctx.overflow) *ctx.overflow = 1;
   pdl_trigger();
 }
@@ -1186,6 +1163,22 @@ static cudaError_t launch_cross_cfg(const CrossAttnArgs& a, ActOut ctx, cudaStre
   return launch_pdl(kern, grid, block, smem, s, a, ctx);
 }
 
+// the tail kernels that read fp16 hi/lo planes written by the EPI_PLANES GEMM epilogue (fp16x3 mode only)
+bool tail_self_attn_reads_planes(int mode) {
+  const char* e = getenv("RB200_SELF_MMA");
+  const char* p = getenv("RB200_TAIL_PLANES");
+  return prec_is_fp16(mode) && !(e && e[0] == '0') && !(p && p[0] == '0');
+}
+bool tail_cross_attn_reads_planes(int mode, int S) {
+  // Measured on B200 (round 2): 256 us with planes vs 232 us with fp32 q rows. The q fragments are read straight from
+  // global memory, and a plane word is a 4-byte load where the fp32 pair was an 8-byte one: twice the load
+  // instructions for the same 16-byte-per-row sectors. Opt-in (RB200_XATTN_PLANES=1) until q is staged through
+  // shared memory with ldmatrix.
+  const char* e = getenv("RB200_XATTN_MMA");
+  const char* p = getenv("RB200_XATTN_PLANES");
+  return prec_is_fp16(mode) && S <= 32 && !(e && e[0] == '0') && (p && p[0] == '1');
+}
+
 int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s) {
   RB_REQUIRE(a.lay.P >= 1 && a.lay.P <= RB_TAIL_MAX_L, "forced tail needs 1 <= P <= %d (P=%d)", RB_TAIL_MAX_L, a.lay.P);
   if (a.R == 0) return 0;
@@ -1194,34 +1187,25 @@ int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s) {
     return !(e && e[0] == '0');
   }();
   const bool mma = use_mma && prec_is_fp16(ctx.mode);      // tensor-core kernel on fp16 planes; FFMA kernel otherwise
-  const char* ve = getenv("RB200_SELF_TAIL");              // v1: the unpipelined tensor-core kernel (A/B measurements)
-  const bool v1 = ve && strcmp(ve, "v1") == 0;
   static bool attr_set = false;
   static int sms = 0;
   if (!attr_set) {
     RB_CUDA(cudaFuncSetAttribute(self_attn_tail_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)((size_t)kWarps * kTailWarpFloats * sizeof(float))));
-    RB_CUDA(cudaFuncSetAttribute(self_attn_tail_mma16_v1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)((size_t)kWarps * kTailMmaWarpBytes)));
     RB_CUDA(cudaFuncSetAttribute(self_attn_tail_mma16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 kTailPipeWarps * kTailPipeWarpBytes));
+                                 (int)((size_t)kWarps * kTailMmaWarpBytes)));
     int dev = 0;
     RB_CUDA(cudaGetDevice(&dev));
     RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
     attr_set = true;
   }
-  if (mma && !v1) {
-    const int want = ceil_div((int64_t)a.R * a.H, kTailPipeWarps);
-    const dim3 grid(want < sms ? want : sms), block(kTailPipeWarps * 32);
-    RB_CUDA(launch_pdl(self_attn_tail_mma16_kernel, grid, block, (size_t)kTailPipeWarps * kTailPipeWarpBytes, s, a, ctx));
-  } else {
-    const size_t smem = mma ? (size_t)kWarps * kTailMmaWarpBytes : (size_t)kWarps * kTailWarpFloats * sizeof(float);
-    const int want = ceil_div((int64_t)a.R * a.H, kWarps);
-    const int per_sm = mma ? 3 : 2;
-    const dim3 grid(want < per_sm * sms ? want : per_sm * sms), block(kWarps * 32);
-    if (mma) RB_CUDA(launch_pdl(self_attn_tail_mma16_v1_kernel, grid, block, smem, s, a, ctx));
-    else RB_CUDA(launch_pdl(self_attn_tail_kernel, grid, block, smem, s, a, ctx));
-  }
+  RB_REQUIRE(a.qkv_hi == nullptr || mma, "q | k | v planes are only read by the tensor-core tail kernel");
+  const size_t smem = mma ? (size_t)kWarps * kTailMmaWarpBytes : (size_t)kWarps * kTailWarpFloats * sizeof(float);
+  const int want = ceil_div((int64_t)a.R * a.H, kWarps);
+  const int per_sm = mma ? 3 : 2;
+  const dim3 grid(want < per_sm * sms ? want : per_sm * sms), block(kWarps * 32);
+  if (mma) RB_CUDA(launch_pdl(self_attn_tail_mma16_kernel, grid, block, smem, s, a, ctx));
+  else RB_CUDA(launch_pdl(self_attn_tail_kernel, grid, block, smem, s, a, ctx));
   launch_count()++;
   return 0;
 }

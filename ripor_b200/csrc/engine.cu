@@ -709,12 +709,20 @@ int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, const rb::TailLa
   RB_REQUIRE(M <= l.Mcap, "forced tail of %lld rows exceeds the workspace capacity %lld", (long long)M, (long long)l.Mcap);
   RB_TRY(rb::launch_tail_prepare(beam, trie, lay, e->in_tab_dev, e->start_emb, l.x, d, s));
   const int32_t* qstart = trie ? beam->qstate : nullptr;
+  const bool self_planes = rb::tail_self_attn_reads_planes(e->mode);
+  const bool cross_planes = rb::tail_cross_attn_reads_planes(e->mode, l.S);
   const int64_t layer_cache = (int64_t)e->Lmodel * l.Rcap * inner;
   for (size_t i = 0; i < e->dec.size(); ++i) {
     Layer& w = e->dec[i];
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln0, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
     rb::TailAttnArgs ta;
+    if (self_planes) {     // q | k | v leave the GEMM as fp16 hi/lo planes (same bytes as the fp32 buffer they replace)
+      RB_TRY(gemm(e, l, l.xn, d, w.qkv, nullptr, 0, e->act(l, l.qkv, 3 * inner), M, rb::EPI_PLANES, s));
+      ta.qkv_hi = reinterpret_cast<const __half*>(l.qkv);
+      ta.qkv_plane = l.Mcap * 3 * inner;
+    } else {
+      RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
+    }
     ta.qkv = l.qkv; ta.cache_k = l.cache_k + i * layer_cache; ta.cache_v = l.cache_v + i * layer_cache;
     ta.anc = beam->fz_anc; ta.bias = e->dec_bias; ta.row_cap = l.Rcap;
     ta.R = nfz_rows; ta.H = e->H; ta.L = e->Lmodel; ta.nb = beam->nb;
@@ -722,8 +730,14 @@ int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, const rb::TailLa
     RB_TRY(rb::launch_self_attn_tail(ta, e->act(l, l.ctx, inner), s));
     RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
     rb::CrossAttnArgs ca;
+    if (cross_planes) {
+      RB_TRY(gemm(e, l, l.xn, d, w.cq, nullptr, 0, e->act(l, l.q2, inner), M, rb::EPI_PLANES, s));
+      ca.q_hi = reinterpret_cast<const __half*>(l.q2);
+      ca.q_plane = l.Mcap * inner;
+    } else {
+      RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
+    }
     ca.q = l.q2; ca.kv = l.cross_kv + (int64_t)i * l.BScap * 2 * inner; ca.ld = 2 * inner; ca.k_off = 0;
     ca.v_off = inner; ca.mask = l.cur_mask; ca.M = nfz_rows; ca.H = e->H; ca.S = l.S; ca.rows_per_query = beam->nb;
     ca.qmap = beam->fz_list; ca.ragged = 1; ca.qstart = qstart; ca.lay = lay;

@@ -453,7 +453,7 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
             }
           }
         }
-      } else if (epilogue != EPI_RELU_ACT) {
+      } else if (epilogue != EPI_RELU_ACT && epilogue != EPI_PLANES) {
         // fp32 output: 32 columns = 128 bytes per staging row
 #pragma unroll 1
         for (int c = 0; c < HALF; c += 32) {
@@ -471,7 +471,8 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tmem_ld32(taddr + (uint32_t)c, r);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float v = fmaxf(__uint_as_float(r[j]) * rowscale, 0.f);
+            const float x = __uint_as_float(r[j]) * rowscale;
+            const float v = epilogue == EPI_RELU_ACT ? fmaxf(x, 0.f) : x;
             const float h = round_tf32(v);
             hi[j] = __float_as_uint(h);
             r[j] = __float_as_uint(round_tf32(v - h));
@@ -490,10 +491,11 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           tmem_ld32(taddr + (uint32_t)(c + 32), r1);
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float a = fmaxf(__uint_as_float(j < 16 ? r0[2 * j] : r1[2 * j - 32]) * rowscale, 0.f);
-            const float b = fmaxf(__uint_as_float(j < 16 ? r0[2 * j + 1] : r1[2 * j - 31]) * rowscale, 0.f);
+            float a = __uint_as_float(j < 16 ? r0[2 * j] : r1[2 * j - 32]) * rowscale;
+            float b = __uint_as_float(j < 16 ? r0[2 * j + 1] : r1[2 * j - 31]) * rowscale;
+            if (epilogue == EPI_RELU_ACT) { a = fmaxf(a, 0.f); b = fmaxf(b, 0.f); }
             if (is_fp16) {
-              bad |= !(a <= kFp16Limit && b <= kFp16Limit);
+              bad |= !(fabsf(a) <= kFp16Limit && fabsf(b) <= kFp16Limit);
               const __half2 h = __floats2half2_rn(a, b);
               const float2 hf = __half22float2(h);
               const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
@@ -556,7 +558,8 @@ int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
   // output maps: boxes of 32 rows x 128 bytes, clipped by TMA at row M / column N.
   //   EPI_STORE / EPI_RESIDUAL: O0 = C            EPI_RELU_ACT: O0, O1 = activation planes
   //   EPI_RESID_NORM: O0 = C, O1, O2 = activation planes
-  const bool planes_out = g.epilogue == EPI_RELU_ACT || g.epilogue == EPI_RESID_NORM;
+  const bool planes_only = g.epilogue == EPI_RELU_ACT || g.epilogue == EPI_PLANES;
+  const bool planes_out = planes_only || g.epilogue == EPI_RESID_NORM;
   if (planes_out) {
     RB_REQUIRE((g.N * ELEM_BYTES) % 16 == 0, "N=%lld: activation rows must be multiples of 16 bytes", (long long)g.N);
     RB_REQUIRE(g.act.base != nullptr, "this epilogue needs an activation output buffer");
@@ -565,7 +568,7 @@ int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
     RB_REQUIRE(g.N % 64 == 0 && g.nf.ss_prev && g.nf.ss_out && g.nf.np == g.N / 64,
                "EPI_RESID_NORM needs N %% 64 == 0 and the NormFold tables (np = N / 64)");
   }
-  if (g.epilogue != EPI_RELU_ACT) RB_TRY(tensor_map_2d(g.C, g.M, g.N, 32, 4, &tmO0, g.ldc));
+  if (!planes_only) RB_TRY(tensor_map_2d(g.C, g.M, g.N, 32, 4, &tmO0, g.ldc));
   if (planes_out) {
     CUtensorMap p0, p1;
     RB_TRY(tensor_map_2d(g.act.base, g.M, g.N, 32, ELEM_BYTES, &p0, g.N));
@@ -573,7 +576,7 @@ int launch_cfg2(const GemmArgs& g, cudaStream_t s) {
     if (cfg::PLANES == 2)
       RB_TRY(tensor_map_2d(static_cast<const char*>(g.act.base) + g.act.plane * ELEM_BYTES, g.M, g.N, 32, ELEM_BYTES,
                            &p1, g.N));
-    if (g.epilogue == EPI_RELU_ACT) { tmO0 = p0; tmO1 = p1; tmO2 = p1; }
+    if (planes_only) { tmO0 = p0; tmO1 = p1; tmO2 = p1; }
     else { tmO1 = p0; tmO2 = p1; }
   } else {
     tmO1 = tmO0;
@@ -630,7 +633,7 @@ int launch_gemm_sm100_2cta(const GemmArgs& g, cudaStream_t s) {
   const int elem = prec_elem_bytes(g.mode);
   RB_REQUIRE(g.K % (16 / elem) == 0, "K=%lld must be a multiple of %d for TMA", (long long)g.K, 16 / elem);
   RB_REQUIRE(g.N % 4 == 0, "N=%lld must be a multiple of 4", (long long)g.N);
-  RB_REQUIRE(g.epilogue == EPI_RELU_ACT || g.ldc % 4 == 0, "ldc must be a multiple of 4");
+  RB_REQUIRE(g.epilogue == EPI_RELU_ACT || g.epilogue == EPI_PLANES || g.ldc % 4 == 0, "ldc must be a multiple of 4");
   if (g.M == 0 || g.N == 0) return 0;
   switch (g.mode) {
     case RB200_PREC_TF32X3: return launch_bn2<4, 3>(g, s);

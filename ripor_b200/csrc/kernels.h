@@ -10,8 +10,10 @@ enum GemmEpilogue {
   EPI_STORE = 0,       // C = acc                       (fp32)
   EPI_RESIDUAL = 1,    // C = C + acc                   (fp32 residual stream)
   EPI_RELU_ACT = 2,    // act_out = relu(acc)           (ActBuf for the next GEMM: DenseReluDense.wi)
-  EPI_RESID_NORM = 3   // C = C + acc, act_out = planes(C / r_prev), ss_out = per-row partial sums of C^2:
+  EPI_RESID_NORM = 3,  // C = C + acc, act_out = planes(C / r_prev), ss_out = per-row partial sums of C^2:
                        // the residual add with the FOLLOWING T5LayerNorm folded in (see NormFold below)
+  EPI_PLANES = 4       // act_out = acc                 (operand planes, no ReLU: the forced tail's q | k | v and
+                       // cross-attention q go straight to the tensor-core attention kernels as fp16 hi/lo planes)
 };
 
 // T5LayerNorm folded into the GEMMs around it (tensor-core modes). rmsnorm(x) * W^T = (1/r) * x * (W diag(ln))^T with
@@ -97,6 +99,9 @@ struct CrossAttnArgs {
   int ragged = 0;
   const int32_t* qstart = nullptr;
   TailLayout lay;
+  // fp16x3 forced tail: q as fp16 hi/lo planes (EPI_PLANES epilogue), row length q_ld (or inner); nullptr: fp32 `q`
+  const __half* q_hi = nullptr;
+  int64_t q_plane = 0;
 };
 int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s);
 
@@ -115,7 +120,13 @@ struct TailAttnArgs {
   const int32_t* fz_list; // frozen slot -> query
   const int32_t* qstart;  // per query: first position of the pass (nullptr: 0 for all, no cached prefix)
   TailLayout lay;
+  // fp16x3 mode: q | k | v of the pass as fp16 hi/lo planes written by the EPI_PLANES GEMM epilogue (hi plane at
+  // qkv_hi, lo plane qkv_plane elements further; same [rows, 3*inner] layout). nullptr: fp32 rows in `qkv`.
+  const __half* qkv_hi = nullptr;
+  int64_t qkv_plane = 0;
 };
+bool tail_self_attn_reads_planes(int mode);
+bool tail_cross_attn_reads_planes(int mode, int S);
 int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s);
 
 // fp32 FFMA GEMM (RB200_PREC_FP32) and the tcgen05 GEMM family (all other modes)

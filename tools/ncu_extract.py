@@ -10,8 +10,12 @@ WANT = {
     "dram__bytes_read.sum": "dram_read",
     "dram__bytes_write.sum": "dram_write",
     "l1tex__m_xbar2l1tex_read_bytes.sum": "l2_to_sm",
-    "sm__pipe_tensor_subpipe_op_utcmma_cycles_active.avg.pct_of_peak_sustained_active": "tensor_pct",
-    "sm__inst_executed_pipe_tensor_op_utcmma.sum": "utcmma",
+    # tensor-pipe activity (tcgen05 MMAs are counted on the hmma sub-pipe by this ncu build)
+    "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed": "tensor_pipe_pct",
+    "TPC.TriageCompute.sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg": "tensor_hmma_cycles",
+    "sm__inst_executed_pipe_tensor_subpipe_hmma.avg.pct_of_peak_sustained_active": "hmma_inst_pct",
+    "lts__t_bytes.sum": "l2_bytes",
+    "sm__cycles_elapsed.max": "sm_cycles",
     "smsp__issue_active.avg.pct_of_peak_sustained_active": "issue_pct",
     "sm__warps_active.avg.pct_of_peak_sustained_active": "warps_pct",
     "dram__throughput.avg.pct_of_peak_sustained_elapsed": "dram_pct",
