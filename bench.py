@@ -56,6 +56,7 @@ def parse_args():
     ap.add_argument("--zipf-parity-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-zipf", action="store_true", help="skip the sibling measurement on the skewed trie")
+    ap.add_argument("--zipf", action="store_true", help="run the skewed-trie sibling under torchrun too")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3/4/5 + topk=1000 block")
     ap.add_argument("--configs-only", default="", help="comma list out of c3,c4,c5,top1000 (default: all)")
     return ap.parse_args()
@@ -449,7 +450,7 @@ def run_ours(a):
                                                         f"leg on {pq} queries"}
     del mask_fn
     # ---- sibling: the same workload on the Zipf-skewed trie (beams reach single leaves at different steps) ----
-    if not a.no_zipf and a.trie == "uniform":
+    if not a.no_zipf and a.trie == "uniform" and (world == 1 or a.zipf):   # (scaling runs: only when asked, --zipf)
         del codes, trie, proc
         zcodes = make_codes(a, "zipf")
         ztrie = DocidTrie.from_codes(zcodes, a.codebook)

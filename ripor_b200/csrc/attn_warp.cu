@@ -759,28 +759,13 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
     const int q0 = tile * 16 + g, q1 = q0 + 8;
     const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64 + 2 * t;
     const float* qr1 = a.q + global_row(min(q1, nrows - 1)) * q_ld + h * 64 + 2 * t;
-    const bool qplanes = a.q_hi != nullptr;                         // q arrives as fp16 hi/lo planes (EPI_PLANES)
-    const __half* qh0 = a.q_hi + global_row(min(q0, nrows - 1)) * q_ld + h * 64 + 2 * t;
-    const __half* qh1 = a.q_hi + global_row(min(q1, nrows - 1)) * q_ld + h * 64 + 2 * t;
     float2 qa[4][4];                                                // A fragments (raw fp32 pairs) of the 4 k-steps
-    uint32_t qph[4][4], qpl[4][4];                                  // ... or the plane words as they are
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      if (qplanes) {
-        qph[kk][0] = __ldg(reinterpret_cast<const uint32_t*>(qh0 + kk * 16));
-        qph[kk][1] = __ldg(reinterpret_cast<const uint32_t*>(qh1 + kk * 16));
-        qph[kk][2] = __ldg(reinterpret_cast<const uint32_t*>(qh0 + kk * 16 + 8));
-        qph[kk][3] = __ldg(reinterpret_cast<const uint32_t*>(qh1 + kk * 16 + 8));
-        qpl[kk][0] = __ldg(reinterpret_cast<const uint32_t*>(qh0 + a.q_plane + kk * 16));
-        qpl[kk][1] = __ldg(reinterpret_cast<const uint32_t*>(qh1 + a.q_plane + kk * 16));
-        qpl[kk][2] = __ldg(reinterpret_cast<const uint32_t*>(qh0 + a.q_plane + kk * 16 + 8));
-        qpl[kk][3] = __ldg(reinterpret_cast<const uint32_t*>(qh1 + a.q_plane + kk * 16 + 8));
-      } else {
-        qa[kk][0] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16));
-        qa[kk][1] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16));
-        qa[kk][2] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16 + 8));
-        qa[kk][3] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16 + 8));
-      }
+      qa[kk][0] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16));
+      qa[kk][1] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16));
+      qa[kk][2] = __ldg(reinterpret_cast<const float2*>(qr0 + kk * 16 + 8));
+      qa[kk][3] = __ldg(reinterpret_cast<const float2*>(qr1 + kk * 16 + 8));
     }
     float sacc[4][4];
 #pragma unroll
@@ -791,10 +776,7 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
     for (int kk = 0; kk < 4; ++kk) {
       uint32_t ah[4], al[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (qplanes) { ah[u] = qph[kk][u]; al[u] = qpl[kk][u]; }
-        else split_h2(qa[kk][u].x, qa[kk][u].y, ah[u], al[u], bad);
-      }
+      for (int u = 0; u < 4; ++u) split_h2(qa[kk][u].x, qa[kk][u].y, ah[u], al[u], bad);
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t;      // words: K[key nt*8+g][dims kk*16 + 2t, +1]
@@ -886,131 +868,172 @@ constexpr int kTailMmaWarpBytes = 4 * 32 * kKLd * 2;          // K hi | K lo | V
 
 // The T queries of one (frozen row, head) task as 16-row m16n8k16 tiles against the staged fp16 K/V planes of its
 // lineage: tile row q = query index (position t + q); causal mask and relative position bias on the score fragments.
-__device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const ActOut& ctx, const __half* k_hi,
-                                                 const __half* k_lo, const __half* v_hi, const __half* v_lo, int rp,
-                                                 int h, int t, int T, bool& bad) {
-  const bool qplanes = a.qkv_hi != nullptr;    // q | k | v arrive as fp16 hi/lo planes (EPI_PLANES): no split here
+// Q fragments (fp16 hi / lo words of the 4 k-steps) of tile `tile` of a task, straight from the planes
+__device__ __forceinline__ void tail_load_q_planes(const TailAttnArgs& a, int rp, int h, int t, int T, int tile,
+                                                   uint32_t (&qh)[4][4], uint32_t (&ql)[4][4]) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int inner = a.H * 64;
+  const int q0 = tile * 16 + g, q1 = q0 + 8;
+  const __half* qh0 = a.qkv_hi + ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+  const __half* qh1 = a.qkv_hi + ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    qh[kk][0] = *reinterpret_cast<const uint32_t*>(qh0 + kk * 16);
+    qh[kk][1] = *reinterpret_cast<const uint32_t*>(qh1 + kk * 16);
+    qh[kk][2] = *reinterpret_cast<const uint32_t*>(qh0 + kk * 16 + 8);
+    qh[kk][3] = *reinterpret_cast<const uint32_t*>(qh1 + kk * 16 + 8);
+    ql[kk][0] = *reinterpret_cast<const uint32_t*>(qh0 + a.qkv_plane + kk * 16);
+    ql[kk][1] = *reinterpret_cast<const uint32_t*>(qh1 + a.qkv_plane + kk * 16);
+    ql[kk][2] = *reinterpret_cast<const uint32_t*>(qh0 + a.qkv_plane + kk * 16 + 8);
+    ql[kk][3] = *reinterpret_cast<const uint32_t*>(qh1 + a.qkv_plane + kk * 16 + 8);
+  }
+}
+
+// same from fp32 q rows, split here (precision modes / paths without planes)
+__device__ __forceinline__ void tail_load_q_f32(const TailAttnArgs& a, int rp, int h, int t, int T, int tile,
+                                                uint32_t (&qh)[4][4], uint32_t (&ql)[4][4], bool& bad) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int inner = a.H * 64;
+  const int q0 = tile * 16 + g, q1 = q0 + 8;
+  const float* qr0 = a.qkv + ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+  const float* qr1 = a.qkv + ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
+#pragma unroll
+  for (int kk = 0; kk < 4; ++kk) {
+    const float2 x0 = *reinterpret_cast<const float2*>(qr0 + kk * 16), x1 = *reinterpret_cast<const float2*>(qr1 + kk * 16);
+    const float2 x2 = *reinterpret_cast<const float2*>(qr0 + kk * 16 + 8);
+    const float2 x3 = *reinterpret_cast<const float2*>(qr1 + kk * 16 + 8);
+    split_h2(x0.x, x0.y, qh[kk][0], ql[kk][0], bad);
+    split_h2(x1.x, x1.y, qh[kk][1], ql[kk][1], bad);
+    split_h2(x2.x, x2.y, qh[kk][2], ql[kk][2], bad);
+    split_h2(x3.x, x3.y, qh[kk][3], ql[kk][3], bad);
+  }
+}
+
+// One 16-row tile of a (frozen row, head) task against the staged fp16 K/V planes of its lineage: tile row q = query
+// index (position t + q); S = Q K^T and O = softmax(S) V on m16n8k16 with the 3-product split, causal mask and
+// relative position bias on the score fragments.
+__device__ __forceinline__ void tail_mma16_tile(const TailAttnArgs& a, const ActOut& ctx, const __half* k_hi,
+                                                const __half* k_lo, const __half* v_hi, const __half* v_lo, int rp,
+                                                int h, int t, int T, int tile, const uint32_t (&qh)[4][4],
+                                                const uint32_t (&ql)[4][4]) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
   const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
   const int vrow = (lane & 7) + 8 * ((lane >> 3) & 1), vcol = 8 * (lane >> 4);   // ldmatrix row of this lane
   const int inner = a.H * 64, L = a.L;
-  // ---- the T queries as 16-row tiles: tile row q = query index (position t + q) --------------------------------
-  for (int tile = 0; tile * 16 < T; ++tile) {
-    const int q0 = tile * 16 + g, q1 = q0 + 8;
-    const int64_t qo0 = ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
-    const int64_t qo1 = ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * 3 * inner + h * 64 + 2 * t4;
-    const float* qr0 = a.qkv + qo0;
-    const float* qr1 = a.qkv + qo1;
-    const __half* qh0 = a.qkv_hi + qo0;
-    const __half* qh1 = a.qkv_hi + qo1;
-    float sacc[4][4];
+  const int q0 = tile * 16 + g, q1 = q0 + 8;
+  float sacc[4][4];
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+  for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) sacc[nt][u] = 0.f;
+    for (int u = 0; u < 4; ++u) sacc[nt][u] = 0.f;
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-      uint32_t ah[4], al[4];
-      if (qplanes) {
-        ah[0] = *reinterpret_cast<const uint32_t*>(qh0 + kk * 16);
-        ah[1] = *reinterpret_cast<const uint32_t*>(qh1 + kk * 16);
-        ah[2] = *reinterpret_cast<const uint32_t*>(qh0 + kk * 16 + 8);
-        ah[3] = *reinterpret_cast<const uint32_t*>(qh1 + kk * 16 + 8);
-        al[0] = *reinterpret_cast<const uint32_t*>(qh0 + a.qkv_plane + kk * 16);
-        al[1] = *reinterpret_cast<const uint32_t*>(qh1 + a.qkv_plane + kk * 16);
-        al[2] = *reinterpret_cast<const uint32_t*>(qh0 + a.qkv_plane + kk * 16 + 8);
-        al[3] = *reinterpret_cast<const uint32_t*>(qh1 + a.qkv_plane + kk * 16 + 8);
-      } else {
-        const float2 x0 = *reinterpret_cast<const float2*>(qr0 + kk * 16), x1 = *reinterpret_cast<const float2*>(qr1 + kk * 16);
-        const float2 x2 = *reinterpret_cast<const float2*>(qr0 + kk * 16 + 8);
-        const float2 x3 = *reinterpret_cast<const float2*>(qr1 + kk * 16 + 8);
-        split_h2(x0.x, x0.y, ah[0], al[0], bad);
-        split_h2(x1.x, x1.y, ah[1], al[1], bad);
-        split_h2(x2.x, x2.y, ah[2], al[2], bad);
-        split_h2(x3.x, x3.y, ah[3], al[3], bad);
-      }
+  for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t4;
-        const uint32_t bh0 = kh32[o0], bh1 = kh32[o0 + 4], bl0 = kl32[o0], bl1 = kl32[o0 + 4];
-        mma_f16(sacc[nt], al, bh0, bh1);
-        mma_f16(sacc[nt], ah, bl0, bl1);
-        mma_f16(sacc[nt], ah, bh0, bh1);
-      }
+    for (int nt = 0; nt < 4; ++nt) {
+      const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t4;
+      const uint32_t bh0 = kh32[o0], bh1 = kh32[o0 + 4], bl0 = kl32[o0], bl1 = kl32[o0 + 4];
+      mma_f16(sacc[nt], ql[kk], bh0, bh1);
+      mma_f16(sacc[nt], qh[kk], bl0, bl1);
+      mma_f16(sacc[nt], qh[kk], bh0, bh1);
     }
-    // causal mask + relative position bias: row q sits at position t + q and sees keys p <= t + q
-    const int pq0 = t + q0, pq1 = t + q1;
-    const float* bias_h = a.bias + h * L;
-    float mx0 = -INFINITY, mx1 = -INFINITY;
+  }
+  // causal mask + relative position bias: row q sits at position t + q and sees keys p <= t + q
+  const int pq0 = t + q0, pq1 = t + q1;
+  const float* bias_h = a.bias + h * L;
+  float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+  for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        const int p = nt * 8 + 2 * t4 + w;
-        sacc[nt][w] = (p <= pq0 && q0 < T) ? sacc[nt][w] + __ldg(bias_h + (pq0 - p)) : -INFINITY;
-        sacc[nt][2 + w] = (p <= pq1 && q1 < T) ? sacc[nt][2 + w] + __ldg(bias_h + (pq1 - p)) : -INFINITY;
-        mx0 = fmaxf(mx0, sacc[nt][w]);
-        mx1 = fmaxf(mx1, sacc[nt][2 + w]);
-      }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    float sum0 = 0.f, sum1 = 0.f;
+    for (int w = 0; w < 2; ++w) {
+      const int p = nt * 8 + 2 * t4 + w;
+      sacc[nt][w] = (p <= pq0 && q0 < T) ? sacc[nt][w] + __ldg(bias_h + (pq0 - p)) : -INFINITY;
+      sacc[nt][2 + w] = (p <= pq1 && q1 < T) ? sacc[nt][2 + w] + __ldg(bias_h + (pq1 - p)) : -INFINITY;
+      mx0 = fmaxf(mx0, sacc[nt][w]);
+      mx1 = fmaxf(mx1, sacc[nt][2 + w]);
+    }
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+  mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+  mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+  float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int nt = 0; nt < 4; ++nt)
+  for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-      for (int w = 0; w < 2; ++w) {
-        sacc[nt][w] = mx0 == -INFINITY ? 0.f : expf(sacc[nt][w] - mx0);
-        sacc[nt][2 + w] = mx1 == -INFINITY ? 0.f : expf(sacc[nt][2 + w] - mx1);
-        sum0 += sacc[nt][w];
-        sum1 += sacc[nt][2 + w];
-      }
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
-    sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
-    sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
-    float oacc[8][4];
+    for (int w = 0; w < 2; ++w) {
+      sacc[nt][w] = mx0 == -INFINITY ? 0.f : expf(sacc[nt][w] - mx0);
+      sacc[nt][2 + w] = mx1 == -INFINITY ? 0.f : expf(sacc[nt][2 + w] - mx1);
+      sum0 += sacc[nt][w];
+      sum1 += sacc[nt][2 + w];
+    }
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 1);
+  sum0 += __shfl_xor_sync(0xffffffffu, sum0, 2);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 1);
+  sum1 += __shfl_xor_sync(0xffffffffu, sum1, 2);
+  float oacc[8][4];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd)
+#pragma unroll
+    for (int u = 0; u < 4; ++u) oacc[nd][u] = 0.f;
+#pragma unroll
+  for (int ks = 0; ks < 2; ++ks) {
+    uint32_t ph[4], pl[4];
+    bool nb_ = false;
+    split_h2(sacc[2 * ks][0], sacc[2 * ks][1], ph[0], pl[0], nb_);
+    split_h2(sacc[2 * ks][2], sacc[2 * ks][3], ph[1], pl[1], nb_);
+    split_h2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ph[2], pl[2], nb_);
+    split_h2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ph[3], pl[3], nb_);
+#pragma unroll
+    for (int nd = 0; nd < 8; nd += 2) {
+      uint32_t bh[4], bl[4];
+      ldmatrix_x4_trans(bh, v_hi + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
+      ldmatrix_x4_trans(bl, v_lo + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
+      mma_f16(oacc[nd], pl, bh[0], bh[1]);
+      mma_f16(oacc[nd], ph, bl[0], bl[1]);
+      mma_f16(oacc[nd], ph, bh[0], bh[1]);
+      mma_f16(oacc[nd + 1], pl, bh[2], bh[3]);
+      mma_f16(oacc[nd + 1], ph, bl[2], bl[3]);
+      mma_f16(oacc[nd + 1], ph, bh[2], bh[3]);
+    }
+  }
+  const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
+  if (q0 < T) {
+    const int64_t base = ((int64_t)a.lay.off[t + q0] + rp) * inner + h * 64 + 2 * t4;
 #pragma unroll
     for (int nd = 0; nd < 8; ++nd)
+      act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
+  }
+  if (q1 < T) {
+    const int64_t base = ((int64_t)a.lay.off[t + q1] + rp) * inner + h * 64 + 2 * t4;
 #pragma unroll
-      for (int u = 0; u < 4; ++u) oacc[nd][u] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks) {
-      uint32_t ph[4], pl[4];
-      bool nb_ = false;
-      split_h2(sacc[2 * ks][0], sacc[2 * ks][1], ph[0], pl[0], nb_);
-      split_h2(sacc[2 * ks][2], sacc[2 * ks][3], ph[1], pl[1], nb_);
-      split_h2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ph[2], pl[2], nb_);
-      split_h2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ph[3], pl[3], nb_);
-#pragma unroll
-      for (int nd = 0; nd < 8; nd += 2) {
-        uint32_t bh[4], bl[4];
-        ldmatrix_x4_trans(bh, v_hi + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
-        ldmatrix_x4_trans(bl, v_lo + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
-        mma_f16(oacc[nd], pl, bh[0], bh[1]);
-        mma_f16(oacc[nd], ph, bl[0], bl[1]);
-        mma_f16(oacc[nd], ph, bh[0], bh[1]);
-        mma_f16(oacc[nd + 1], pl, bh[2], bh[3]);
-        mma_f16(oacc[nd + 1], ph, bl[2], bl[3]);
-        mma_f16(oacc[nd + 1], ph, bh[2], bh[3]);
-      }
+    for (int nd = 0; nd < 8; ++nd)
+      act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
+  }
+}
+
+// all tiles of a task; with planes the next tile's Q words are requested before the current tile computes
+__device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const ActOut& ctx, const __half* k_hi,
+                                                 const __half* k_lo, const __half* v_hi, const __half* v_lo, int rp,
+                                                 int h, int t, int T, bool& bad) {
+  uint32_t qh[4][4], ql[4][4];
+  if (a.qkv_hi == nullptr) {
+    for (int tile = 0; tile * 16 < T; ++tile) {
+      tail_load_q_f32(a, rp, h, t, T, tile, qh, ql, bad);
+      tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, tile, qh, ql);
     }
-    const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
-    if (q0 < T) {
-      const int64_t base = ((int64_t)a.lay.off[t + q0] + rp) * inner + h * 64 + 2 * t4;
-#pragma unroll
-      for (int nd = 0; nd < 8; ++nd)
-        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
-    }
-    if (q1 < T) {
-      const int64_t base = ((int64_t)a.lay.off[t + q1] + rp) * inner + h * 64 + 2 * t4;
-#pragma unroll
-      for (int nd = 0; nd < 8; ++nd)
-        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
-    }
+    return;
+  }
+  tail_load_q_planes(a, rp, h, t, T, 0, qh, ql);
+  if (T > 16) {                               // at most two tiles (P <= 32)
+    uint32_t qh1[4][4], ql1[4][4];
+    tail_load_q_planes(a, rp, h, t, T, 1, qh1, ql1);
+    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, 0, qh, ql);
+    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, 1, qh1, ql1);
+  } else {
+    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, 0, qh, ql);
   }
 }
 
@@ -1169,16 +1192,6 @@ bool tail_self_attn_reads_planes(int mode) {
   const char* p = getenv("RB200_TAIL_PLANES");
   return prec_is_fp16(mode) && !(e && e[0] == '0') && !(p && p[0] == '0');
 }
-bool tail_cross_attn_reads_planes(int mode, int S) {
-  // Measured on B200 (round 2): 256 us with planes vs 232 us with fp32 q rows. The q fragments are read straight from
-  // global memory, and a plane word is a 4-byte load where the fp32 pair was an 8-byte one: twice the load
-  // instructions for the same 16-byte-per-row sectors. Opt-in (RB200_XATTN_PLANES=1) until q is staged through
-  // shared memory with ldmatrix.
-  const char* e = getenv("RB200_XATTN_MMA");
-  const char* p = getenv("RB200_XATTN_PLANES");
-  return prec_is_fp16(mode) && S <= 32 && !(e && e[0] == '0') && (p && p[0] == '1');
-}
-
 int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s) {
   RB_REQUIRE(a.lay.P >= 1 && a.lay.P <= RB_TAIL_MAX_L, "forced tail needs 1 <= P <= %d (P=%d)", RB_TAIL_MAX_L, a.lay.P);
   if (a.R == 0) return 0;

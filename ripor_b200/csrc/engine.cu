@@ -710,7 +710,6 @@ int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, const rb::TailLa
   RB_TRY(rb::launch_tail_prepare(beam, trie, lay, e->in_tab_dev, e->start_emb, l.x, d, s));
   const int32_t* qstart = trie ? beam->qstate : nullptr;
   const bool self_planes = rb::tail_self_attn_reads_planes(e->mode);
-  const bool cross_planes = rb::tail_cross_attn_reads_planes(e->mode, l.S);
   const int64_t layer_cache = (int64_t)e->Lmodel * l.Rcap * inner;
   for (size_t i = 0; i < e->dec.size(); ++i) {
     Layer& w = e->dec[i];
@@ -730,14 +729,8 @@ int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, const rb::TailLa
     RB_TRY(rb::launch_self_attn_tail(ta, e->act(l, l.ctx, inner), s));
     RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
     RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
     rb::CrossAttnArgs ca;
-    if (cross_planes) {
-      RB_TRY(gemm(e, l, l.xn, d, w.cq, nullptr, 0, e->act(l, l.q2, inner), M, rb::EPI_PLANES, s));
-      ca.q_hi = reinterpret_cast<const __half*>(l.q2);
-      ca.q_plane = l.Mcap * inner;
-    } else {
-      RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
-    }
     ca.q = l.q2; ca.kv = l.cross_kv + (int64_t)i * l.BScap * 2 * inner; ca.ld = 2 * inner; ca.k_off = 0;
     ca.v_off = inner; ca.mask = l.cur_mask; ca.M = nfz_rows; ca.H = e->H; ca.S = l.S; ca.rows_per_query = beam->nb;
     ca.qmap = beam->fz_list; ca.ragged = 1; ca.qstart = qstart; ca.lay = lay;

@@ -99,9 +99,6 @@ struct CrossAttnArgs {
   int ragged = 0;
   const int32_t* qstart = nullptr;
   TailLayout lay;
-  // fp16x3 forced tail: q as fp16 hi/lo planes (EPI_PLANES epilogue), row length q_ld (or inner); nullptr: fp32 `q`
-  const __half* q_hi = nullptr;
-  int64_t q_plane = 0;
 };
 int launch_cross_attn_decode(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s);
 
@@ -126,7 +123,6 @@ struct TailAttnArgs {
   int64_t qkv_plane = 0;
 };
 bool tail_self_attn_reads_planes(int mode);
-bool tail_cross_attn_reads_planes(int mode, int S);
 int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s);
 
 // fp32 FFMA GEMM (RB200_PREC_FP32) and the tcgen05 GEMM family (all other modes)

@@ -276,7 +276,10 @@ def build_list_smtid_to_nextids(docid_to_smtids):
 
 
 def ddp_setup():
+    """reference evaluate.py:181-182 (init_process_group("nccl")); one process per GPU, the device follows LOCAL_RANK."""
     if "RANK" in os.environ and not torch.distributed.is_initialized():
+        if torch.cuda.is_available():
+            torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
         torch.distributed.init_process_group(backend="nccl" if torch.cuda.is_available() else "gloo")
 
 
