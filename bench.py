@@ -338,6 +338,8 @@ def run_ours(a):
     torch.cuda.synchronize()
     gm, gf, gl = C.c_double(), C.c_double(), C.c_int64()
     _lib.check(lib.rb200_engine_get_profile(eng.h, C.byref(gm), C.byref(gf), C.byref(gl)))
+    gb = C.c_double()
+    _lib.check(lib.rb200_engine_get_profile_bytes(eng.h, C.byref(gb)))
     _lib.check(lib.rb200_engine_set_profiling(eng.h, 0))
     peaks = {}
     try:
@@ -356,6 +358,8 @@ def run_ours(a):
         pass
     roofline = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_note": traffic_note,
+                "algorithmic_bytes_per_launch": gb.value / max(gl.value, 1),
+                "hbm_gbs_of_gemms": gb.value / (gm.value / 1e3) / 1e9 if gm.value > 0 else None,
                 "kernel": f"gemm_sm100_2cta_kernel[{prec}]" if prec != "fp32" else "gemm_simt_kernel",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                 if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",

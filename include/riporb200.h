@@ -275,6 +275,9 @@ int rb200_engine_last_freeze_histogram(const rb200_engine* eng, int32_t* frozen_
  * (ms), the algorithmic FLOPs (2*M*N*K per launch) and the launch count since profiling was switched on. */
 int rb200_engine_set_profiling(rb200_engine* eng, int on);
 int rb200_engine_get_profile(rb200_engine* eng, double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+/* algorithmic HBM bytes of the same launches: operand planes read + result written (a residual add counts the old
+ * value's read and the new value's write; both are done by L2's reduce-add). */
+int rb200_engine_get_profile_bytes(const rb200_engine* eng, double* gemm_bytes);
 
 /* One GEMM of the engine's family, for kernel-level parity tests and the roofline microbench:
  * C[M,N] = A[M,K] * W[N,K]^T (+ C if accumulate) in the given precision. A, W, C fp32 device, row-major. */

@@ -88,6 +88,7 @@ SIGNATURES = {
     "rb200_engine_last_tail_step": (C.c_int, [c_void_p]),
     "rb200_engine_set_profiling": (C.c_int, [c_void_p, C.c_int]),
     "rb200_engine_get_profile": (C.c_int, [c_void_p, P(c_f64), P(c_f64), P(c_i64)]),
+    "rb200_engine_get_profile_bytes": (C.c_int, [c_void_p, P(c_f64)]),
     "rb200_relative_position_bucket": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int]),
     "rb200_gemm_bench": (C.c_int, [C.c_int, c_i64, c_i64, c_i64, C.c_int, C.c_int, C.c_int, P(c_f64), c_void_p]),
     "rb200_gemm": (C.c_int, [C.c_int, c_void_p, c_void_p, c_void_p, c_i64, c_i64, c_i64, C.c_int, C.c_int, c_void_p]),

@@ -196,7 +196,16 @@ __device__ __forceinline__ void cta_prepare(const StepArgs& a, int b, int bc, do
   __syncthreads();
 }
 
-// float64 candidate value of (beam i, token v): s + (1 - mask) * (-1e9) + beam_score, NaN ranked last
+// float64 candidate value of (beam i, token v) with logit x: s + (1 - mask) * (-1e9) + beam_score, NaN ranked last
+__device__ __forceinline__ double cand_value_x(const StepArgs& a, float x, int i, int v, const double* bs,
+                                               const uint32_t* allow, const float* row_max, const float* row_log) {
+  if (a.apply_ls) x = (x - row_max[i]) - row_log[i];
+  const bool ok = (allow[i * a.tv.words + (v >> 5)] >> (v & 31)) & 1u;
+  const double processed = ok ? (double)x : (double)x + (-1e9);
+  const double val = processed + bs[i];
+  return val == val ? val : kNanRank;
+}
+
 __device__ __forceinline__ double cand_value(const StepArgs& a, int bc, int i, int v, const double* bs,
                                              const uint32_t* allow, const float* row_max, const float* row_log) {
   float x = a.logits[(int64_t)(bc * a.rpq + (a.rpq == 1 ? 0 : i)) * a.tv.V + v];
@@ -562,24 +571,39 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   int* lc = list_c + lane * kListLd;
   int cnt = 0;
   {
-    // walk (beam i, token v) with flat index c = i * V + v = lane + 32 k without divisions
+    // walk (beam i, token v) with flat index c = i * V + v = lane + 32 k without divisions. The logits of kBatch
+    // candidates are requested before any of them is ranked: the insertion below is data dependent, and with one load
+    // per iteration every candidate would pay a full trip to HBM (80 serial trips per lane at nb = 10, V = 256).
+    constexpr int kBatch = 8;
     int i = 0, v = lane;
     while (v >= V) { v -= V; ++i; }
-    for (int c = lane; c < total; c += 32) {
-      const double val = cand_value(a, bc, i, v, bs, allow, row_max, row_log);
-      if (cnt < nb || cand_better(val, c, lv[cnt - 1], lc[cnt - 1])) {
-        int pos = cnt < nb ? cnt : nb - 1;                              // a full list drops its last entry
-        while (pos > 0 && cand_better(val, c, lv[pos - 1], lc[pos - 1])) {
-          lv[pos] = lv[pos - 1];
-          lc[pos] = lc[pos - 1];
-          --pos;
-        }
-        lv[pos] = val;
-        lc[pos] = c;
-        if (cnt < nb) ++cnt;
+    for (int c0 = lane; c0 < total; c0 += 32 * kBatch) {
+      float xs[kBatch];
+      int is[kBatch], vs[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        is[u] = i; vs[u] = v;
+        xs[u] = (c0 + 32 * u < total) ? a.logits[(int64_t)(bc * a.rpq + (a.rpq == 1 ? 0 : i)) * V + v] : 0.f;
+        v += 32;
+        while (v >= V) { v -= V; ++i; }
       }
-      v += 32;
-      while (v >= V) { v -= V; ++i; }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int c = c0 + 32 * u;
+        if (c >= total) break;
+        const double val = cand_value_x(a, xs[u], is[u], vs[u], bs, allow, row_max, row_log);
+        if (cnt < nb || cand_better(val, c, lv[cnt - 1], lc[cnt - 1])) {
+          int pos = cnt < nb ? cnt : nb - 1;                              // a full list drops its last entry
+          while (pos > 0 && cand_better(val, c, lv[pos - 1], lc[pos - 1])) {
+            lv[pos] = lv[pos - 1];
+            lc[pos] = lc[pos - 1];
+            --pos;
+          }
+          lv[pos] = val;
+          lc[pos] = c;
+          if (cnt < nb) ++cnt;
+        }
+      }
     }
   }
   // ---- B2. nb rounds of warp arg-max over the list heads ---------------------------------------------------------

@@ -94,7 +94,7 @@ struct rb200_engine {
   bool profiling = false;
   std::vector<cudaEvent_t> events;
   size_t ev_used = 0;
-  double prof_flops = 0.0;
+  double prof_flops = 0.0, prof_bytes = 0.0;
 
   int* overflow = nullptr;         // device flags: [0] activation overflow of the batch in flight, [1] weights
   // forced tail (beam.h): once every beam sits on a single trie leaf, the remaining positions run as one pass
@@ -167,6 +167,14 @@ int gemm(rb200_engine* e, const Lane& l, const void* A, int64_t a_row_len, const
   RB_CUDA(cudaEventRecord(e->events[e->ev_used + 1], s));
   e->ev_used += 2;
   e->prof_flops += 2.0 * (double)M * (double)w.N * (double)w.K;
+  {   // algorithmic HBM bytes of this launch: operand planes in, result out (the residual is read and written by L2)
+    const double pe = (double)e->planes * e->elem, mn = (double)M * (double)w.N;
+    double out = 4.0 * mn;
+    if (epi == rb::EPI_RESIDUAL) out = 8.0 * mn;
+    else if (epi == rb::EPI_RELU_ACT || epi == rb::EPI_PLANES) out = pe * mn;
+    else if (epi == rb::EPI_RESID_NORM) out = 8.0 * mn + pe * mn;
+    e->prof_bytes += pe * ((double)M * (double)w.K + (double)w.N * (double)w.K) + out;
+  }
   return st;
 }
 
@@ -711,44 +719,70 @@ int lane_tail(rb200_engine* e, Lane& l, const rb200_trie* trie, const rb::TailLa
   const int32_t* qstart = trie ? beam->qstate : nullptr;
   const bool self_planes = rb::tail_self_attn_reads_planes(e->mode);
   const int64_t layer_cache = (int64_t)e->Lmodel * l.Rcap * inner;
+  // NormFold chain (RB200_FOLD=1): the layer norms live in the GEMM epilogues around them, see lane_encode
+  int fp = 0;
+  auto consumer = [&](int64_t row0 = 0) {
+    rb::NormFold nf;
+    if (!e->fold) return nf;
+    nf.ss_prev = l.ss[fp ^ 1] + row0 * e->np; nf.ss_cur = l.ss[fp] + row0 * e->np; nf.np = e->np;
+    nf.inv_d = 1.0f / (float)d; nf.eps = eps; nf.scaled = true;
+    return nf;
+  };
+  auto producer = [&]() {
+    rb::NormFold nf;
+    nf.ss_prev = l.ss[fp]; nf.ss_out = l.ss[fp ^ 1]; nf.np = e->np; nf.inv_d = 1.0f / (float)d; nf.eps = eps;
+    fp ^= 1;
+    return nf;
+  };
+  // residual add (+ the following layer norm when folded, else a separate RMSNorm launch before the next GEMM)
+  auto residual = [&](const void* A, int64_t a_len, const Packed& w) {
+    if (e->fold) return gemm(e, l, A, a_len, w, l.x, d, e->act(l, l.xn, d), M, rb::EPI_RESID_NORM, s, producer());
+    return gemm(e, l, A, a_len, w, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s);
+  };
+  auto norm = [&](const float* ln) {
+    if (e->fold) return 0;
+    return rb::launch_rmsnorm(l.x, ln, e->act(l, l.xn, d), M, d, eps, 1.0f, s);
+  };
+  if (e->fold) RB_TRY(rb::launch_norm_init(l.x, e->act(l, l.xn, d), l.ss[0], l.ss[1], e->np, M, d, eps, s));
   for (size_t i = 0; i < e->dec.size(); ++i) {
     Layer& w = e->dec[i];
-    RB_TRY(rb::launch_rmsnorm(l.x, w.ln0, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
+    RB_TRY(norm(w.ln0));
     rb::TailAttnArgs ta;
     if (self_planes) {     // q | k | v leave the GEMM as fp16 hi/lo planes (same bytes as the fp32 buffer they replace)
-      RB_TRY(gemm(e, l, l.xn, d, w.qkv, nullptr, 0, e->act(l, l.qkv, 3 * inner), M, rb::EPI_PLANES, s));
+      RB_TRY(gemm(e, l, l.xn, d, w.qkv, nullptr, 0, e->act(l, l.qkv, 3 * inner), M, rb::EPI_PLANES, s, consumer()));
       ta.qkv_hi = reinterpret_cast<const __half*>(l.qkv);
       ta.qkv_plane = l.Mcap * 3 * inner;
     } else {
-      RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s));
+      RB_TRY(gemm(e, l, l.xn, d, w.qkv, l.qkv, 3 * inner, ActOut{}, M, rb::EPI_STORE, s, consumer()));
     }
     ta.qkv = l.qkv; ta.cache_k = l.cache_k + i * layer_cache; ta.cache_v = l.cache_v + i * layer_cache;
     ta.anc = beam->fz_anc; ta.bias = e->dec_bias; ta.row_cap = l.Rcap;
     ta.R = nfz_rows; ta.H = e->H; ta.L = e->Lmodel; ta.nb = beam->nb;
     ta.fz_list = beam->fz_list; ta.qstart = qstart; ta.lay = lay;
     RB_TRY(rb::launch_self_attn_tail(ta, e->act(l, l.ctx, inner), s));
-    RB_TRY(gemm(e, l, l.ctx, inner, w.o, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
-    RB_TRY(rb::launch_rmsnorm(l.x, w.ln1, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s));
+    RB_TRY(residual(l.ctx, inner, w.o));
+    RB_TRY(norm(w.ln1));
+    RB_TRY(gemm(e, l, l.xn, d, w.cq, l.q2, inner, ActOut{}, M, rb::EPI_STORE, s, consumer()));
     rb::CrossAttnArgs ca;
     ca.q = l.q2; ca.kv = l.cross_kv + (int64_t)i * l.BScap * 2 * inner; ca.ld = 2 * inner; ca.k_off = 0;
     ca.v_off = inner; ca.mask = l.cur_mask; ca.M = nfz_rows; ca.H = e->H; ca.S = l.S; ca.rows_per_query = beam->nb;
     ca.qmap = beam->fz_list; ca.ragged = 1; ca.qstart = qstart; ca.lay = lay;
     RB_TRY(rb::launch_cross_attn_decode(ca, e->act(l, l.ctx, inner), s));
-    RB_TRY(gemm(e, l, l.ctx, inner, w.co, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
-    RB_TRY(rb::launch_rmsnorm(l.x, w.ln2, e->act(l, l.xn, d), M, d, eps, 1.0f, s));
-    RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), M, rb::EPI_RELU_ACT, s));
-    RB_TRY(gemm(e, l, l.hbuf, dff, w.wo, l.x, d, ActOut{}, M, rb::EPI_RESIDUAL, s));
+    RB_TRY(residual(l.ctx, inner, w.co));
+    RB_TRY(norm(w.ln2));
+    RB_TRY(gemm(e, l, l.xn, d, w.wi, nullptr, 0, e->act(l, l.hbuf, dff), M, rb::EPI_RELU_ACT, s, consumer()));
+    RB_TRY(residual(l.hbuf, dff, w.wo));
   }
   const float scale = e->cfg.scaleup_output_hidden ? 1.0f / sqrtf((float)d) : 1.0f;
-  RB_TRY(rb::launch_rmsnorm(l.x, e->dec_final_ln, e->act(l, l.xn, d), M, d, eps, scale, s));
+  // (folded: the final layer norm and the optional d^-1/2 live in the packed output tables)
+  if (!e->fold) RB_TRY(rb::launch_rmsnorm(l.x, e->dec_final_ln, e->act(l, l.xn, d), M, d, eps, scale, s));
   if (hidden_out) RB_TRY(rb::launch_rmsnorm_f32(l.x, e->dec_final_ln, hidden_out, M, d, eps, s, scale));
   // LM head: the output table differs per position -> one GEMM per position block
   for (int p = 0; p < lay.P; ++p) {
     const int64_t n_p = lay.off[p + 1] - lay.off[p];
     if (n_p == 0) continue;
     RB_TRY(gemm(e, l, static_cast<const char*>(l.xn) + (int64_t)lay.off[p] * d * e->elem, d, e->out_tab[p],
-                l.logits + (int64_t)lay.off[p] * e->V, e->V, ActOut{}, n_p, rb::EPI_STORE, s));
+                l.logits + (int64_t)lay.off[p] * e->V, e->V, ActOut{}, n_p, rb::EPI_STORE, s, consumer(lay.off[p])));
   }
   return 0;
 }
@@ -854,7 +888,7 @@ int rb200_engine_search(rb200_engine* e, const rb200_trie* trie, const int64_t* 
   // (their remaining tokens are determined by the trie) and leave the step loop; the loop goes on with the others as
   // a compacted batch. The host reads two counters back per step (stepping / frozen) to size the next launches.
   const int P = max_new_tokens;
-  const bool try_tail = e->tail && !e->fold && P <= RB_TAIL_MAX_L;
+  const bool try_tail = e->tail && P <= RB_TAIL_MAX_L;
   e->last_tail_from = -1;
   e->last_tail_rows = 0;
   for (int t = 0; t <= RB_TAIL_MAX_L; ++t) e->frozen_at[t] = 0;
@@ -971,6 +1005,13 @@ int rb200_engine_set_profiling(rb200_engine* e, int on) {
   e->profiling = on != 0;
   e->ev_used = 0;
   e->prof_flops = 0.0;
+  e->prof_bytes = 0.0;
+  return 0;
+}
+
+int rb200_engine_get_profile_bytes(const rb200_engine* e, double* gemm_bytes) {
+  RB_REQUIRE(e && gemm_bytes, "null argument");
+  *gemm_bytes = e->prof_bytes;
   return 0;
 }
 
