@@ -366,12 +366,24 @@ __global__ void __launch_bounds__(kSelThreads) beam_step_select_kernel(const Ste
 
   // walk this thread's candidates c = tid + k * THREADS as (beam i, token v) without divisions
   auto for_each_cand = [&](auto&& fn) {
+    constexpr int kBatch = 4;                  // logits of kBatch candidates in flight before any is consumed
     int i = 0, v = tid;
     while (v >= V) { v -= V; ++i; }
-    for (int c = tid; c < total; c += kSelThreads) {
-      fn(c, f64_key(cand_value(a, bc, i, v, bs, allow, row_max, row_log)));
-      v += kSelThreads;
-      while (v >= V) { v -= V; ++i; }
+    for (int c0 = tid; c0 < total; c0 += kSelThreads * kBatch) {
+      float xs[kBatch];
+      int is[kBatch], vs[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        is[u] = i; vs[u] = v;
+        xs[u] = (c0 + kSelThreads * u < total) ? a.logits[(int64_t)(bc * a.rpq + (a.rpq == 1 ? 0 : i)) * V + v] : 0.f;
+        v += kSelThreads;
+        while (v >= V) { v -= V; ++i; }
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int c = c0 + kSelThreads * u;
+        if (c < total) fn(c, f64_key(cand_value_x(a, xs[u], is[u], vs[u], bs, allow, row_max, row_log)));
+      }
     }
   };
   // digit D of the histogram with count(> D) < need <= count(>= D) (from_top) or count(< D) < need <= count(<= D);
