@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--no-zipf", action="store_true", help="skip the sibling measurement on the skewed trie")
     ap.add_argument("--zipf", action="store_true", help="run the skewed-trie sibling under torchrun too")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3/4/5 + topk=1000 block")
-    ap.add_argument("--configs-only", default="", help="comma list out of c3,c4,c5,top1000 (default: all)")
+    ap.add_argument("--configs-only", default="", help="comma list out of c3,c4,c5,top1000,rank4x100 (default: all)")
     return ap.parse_args()
 
 
@@ -469,7 +469,8 @@ def run_ours(a):
         del zcodes, ztrie, zproc, zout
     # ---- the other BASELINE configs + the reference's shipped launch, bounded (2 steps each) ----
     if not a.no_configs and a.trie == "uniform" and (a.model, nb, L, a.codebook) == ("t5-base", 10, 32, 256):
-        want = [c for c in a.configs_only.split(",") if c] or (["c3"] if world > 1 else ["c3", "c4", "c5", "top1000"])
+        want = [c for c in a.configs_only.split(",") if c] or \
+            (["c3"] if world > 1 else ["c3", "top1000", "rank4x100", "c4", "c5"])
         result["configs"] = run_configs(a, want, model, w, dims, measure, rank, world)
     if rank == 0:
         print(json.dumps(result), flush=True)
@@ -497,24 +498,28 @@ def run_configs(a, want, base_model, base_w, base_dims, measure, rank, world):
                    nb=10, B=256, pq=4),
         "top1000": dict(name="reference's shipped eval launch: t5-base, batch_size=1, topk=1000, L=32", model="t5-base",
                         L=32, V=256, nb=1000, B=1, pq=0),
+        # full_scripts/full_evaluate_t5seq_aq_encoder.sh:128-139: t5seq_aq_get_qid_to_smtid_rankdata, DocID prefixes
+        "rank4x100": dict(name="reference's shipped training-data launch: t5-base, batch_size=4, topk=100, "
+                               "max_new_token=16 (prefix search over the 32-code trie)", model="t5-base", L=16, trie_L=32,
+                          V=256, nb=100, B=4, pq=2),
     }
     out = {}
     tries = {}
     for key in want:
         c = table[key]
         try:
-            tk = (c["L"], c["V"])
+            tk = (c.get("trie_L", c["L"]), c["V"])
             if tk not in tries:
                 tries.clear()                      # one 8.8M-doc trie in host memory at a time
-                codes = syn.make_codes(a.docs, c["L"], c["V"])
+                codes = syn.make_codes(a.docs, tk[0], c["V"])
                 tries[tk] = (codes, PrefixConstrainLogitProcessorFastSparse.from_trie(DocidTrie.from_codes(codes, c["V"])))
             codes, proc = tries[tk]
-            if (c["model"], c["L"], c["V"]) == ("t5-base", base_dims.docid_len, base_dims.decoder_vocab_size):
+            if (c["model"], tk[0], c["V"]) == ("t5-base", base_dims.docid_len, base_dims.decoder_vocab_size):
                 model, w, dims = base_model, base_w, base_dims
             else:
                 for p in list(base_model.base_model._engines):       # make room: free the default model's engines
                     base_model.base_model.drop_engine(p)
-                dims = dims_for(c["model"], c["L"], c["V"])
+                dims = dims_for(c["model"], tk[0], c["V"])
                 w = syn.make_weights(dims)
                 model = T5SeqAQEncoder.from_weights(dims, w).to(dev)
             res, o, ids, mask = measure(model, proc, c["B"], c["nb"], c["L"], a.src_len, 2, 1, a.precision, seed_off=1000)

@@ -578,15 +578,17 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   }
   __syncwarp();
 
-  // ---- B1. every lane: sorted list of its best nb candidates -------------------------------------------------------
+  // ---- B1. every lane: sorted list of its best candidates ------------------------------------------------------------
+  // Two passes over the lane's candidates (flat index c = i * V + v = lane + 32 k, walked without divisions; logits
+  // requested kBatch at a time). Pass 1 only tracks the lane's best value; the nb-th largest of the 32 lane maxima is
+  // a lower bound tau of the query's nb-th best candidate (they are nb real candidates). Pass 2 inserts only
+  // candidates >= tau into the lane's sorted list, so the data-dependent insertion - which a warp pays at the depth
+  // of its slowest lane - runs for a few dozen candidates per query instead of for all nb * V of them.
   double* lv = list_v + lane * kListLd;
   int* lc = list_c + lane * kListLd;
   int cnt = 0;
-  {
-    // walk (beam i, token v) with flat index c = i * V + v = lane + 32 k without divisions. The logits of kBatch
-    // candidates are requested before any of them is ranked: the insertion below is data dependent, and with one load
-    // per iteration every candidate would pay a full trip to HBM (80 serial trips per lane at nb = 10, V = 256).
-    constexpr int kBatch = 8;
+  constexpr int kBatch = 8;
+  auto scan = [&](auto&& fn) {
     int i = 0, v = lane;
     while (v >= V) { v -= V; ++i; }
     for (int c0 = lane; c0 < total; c0 += 32 * kBatch) {
@@ -602,22 +604,39 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
         const int c = c0 + 32 * u;
-        if (c >= total) break;
-        const double val = cand_value_x(a, xs[u], is[u], vs[u], bs, allow, row_max, row_log);
-        if (cnt < nb || cand_better(val, c, lv[cnt - 1], lc[cnt - 1])) {
-          int pos = cnt < nb ? cnt : nb - 1;                              // a full list drops its last entry
-          while (pos > 0 && cand_better(val, c, lv[pos - 1], lc[pos - 1])) {
-            lv[pos] = lv[pos - 1];
-            lc[pos] = lc[pos - 1];
-            --pos;
-          }
-          lv[pos] = val;
-          lc[pos] = c;
-          if (cnt < nb) ++cnt;
-        }
+        if (c < total) fn(c, cand_value_x(a, xs[u], is[u], vs[u], bs, allow, row_max, row_log));
       }
     }
+  };
+  double tau = -INFINITY;
+  if (total > 32 * nb) {                       // (with few candidates per lane the filter saves nothing)
+    double mine = -INFINITY;
+    scan([&](int, double val) { mine = val > mine ? val : mine; });
+    for (int j = 0; j < nb; ++j) {             // nb-th largest of the lane maxima: nb arg-max rounds with removal
+      double m = mine;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const double om = __shfl_xor_sync(0xffffffffu, m, o);
+        m = om > m ? om : m;
+      }
+      tau = m;
+      const unsigned owners = __ballot_sync(0xffffffffu, mine == m);
+      if (lane == __ffs(owners) - 1) mine = -INFINITY;        // remove ONE holder of the maximum
+    }
   }
+  scan([&](int c, double val) {
+    if (val >= tau && (cnt < nb || cand_better(val, c, lv[cnt - 1], lc[cnt - 1]))) {
+      int pos = cnt < nb ? cnt : nb - 1;                              // a full list drops its last entry
+      while (pos > 0 && cand_better(val, c, lv[pos - 1], lc[pos - 1])) {
+        lv[pos] = lv[pos - 1];
+        lc[pos] = lc[pos - 1];
+        --pos;
+      }
+      lv[pos] = val;
+      lc[pos] = c;
+      if (cnt < nb) ++cnt;
+    }
+  });
   // ---- B2. nb rounds of warp arg-max over the list heads ---------------------------------------------------------
   int hd = 0;
   for (int j = 0; j < nb; ++j) {

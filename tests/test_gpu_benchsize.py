@@ -114,3 +114,39 @@ def test_shipped_launch_topk1000_batch1_t5base_dims():
     # reported apart from real mismatches (hard part 1)
     real, near = helpers.compare_ranked_near_tie(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, trace)
     assert real == 0, (real, near)
+
+
+def test_config5_16x1024_t5base_dims():
+    """BASELINE configs[4] at real dimensions: t5-base with 16 codebooks of 1024 codes (full_16_1024_scripts), beam 10,
+    8.8 M-doc trie with 2-byte codes; 8 queries."""
+    B, nb, L, V = 8, 10, 16, 1024
+    dims = syn.T5Dims.t5_base(docid_len=L, decoder_vocab_size=V)
+    w = syn.make_weights(dims)
+    codes = syn.make_codes(N_DOCS, L, V)
+    ids, mask = syn.make_queries(B, S=32, seed=904)
+    ref_seq, ref_sc = _oracle(w, dims, codes, V, ids, mask, nb, L)
+    model = T5SeqAQEncoder.from_weights(dims, w)
+    out = _engine_search(model, DocidTrie.from_codes(codes, V), ids, mask, nb, L, precision="auto")
+    assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0
+    assert sum(out.frozen_at_step) == B
+
+
+def test_shipped_training_data_launch_prefix_search():
+    """full_scripts/full_evaluate_t5seq_aq_encoder.sh:128-139 (t5seq_aq_get_qid_to_smtid_rankdata: --batch_size=4
+    --topk=100 --max_new_token=8) at t5-base dimensions: a PREFIX search (8 of the trie's 32 positions), so the ranked
+    rows are leaf ranges that may hold several documents."""
+    B, nb, L, V = 4, 100, 8, 256
+    dims, w = _t5base()
+    codes = _codes("uniform")
+    ids, mask = syn.make_queries(B, S=32, seed=905)
+    ref_seq, ref_sc = _oracle(w, dims, codes, V, ids, mask, nb, L)
+    model = T5SeqAQEncoder.from_weights(dims, w)
+    trie = DocidTrie.from_codes(codes, V)
+    out = _engine_search(model, trie, ids, mask, nb, L, precision="auto")
+    assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0
+    # every ranked prefix exists in the collection: its leaf range is not empty and spells the prefix
+    leaf = out.leaf_ranges.cpu()
+    assert torch.all(leaf[:, 1] > leaf[:, 0])
+    r = 7
+    rows = trie.rows_for_range(int(leaf[r, 0]), int(leaf[r, 1]))
+    assert len(rows) >= 1 and np.all(codes[rows][:, :L] == out.sequences[r, 1:].cpu().numpy())
