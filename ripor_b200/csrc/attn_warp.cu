@@ -759,10 +759,6 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma16_kernel(CrossAttnArgs 
     const int q0 = tile * 16 + g, q1 = q0 + 8;
     const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64 + 2 * t;
     const float* qr1 = a.q + global_row(min(q1, nrows - 1)) * q_ld + h * 64 + 2 * t;
-    if ((tile + 4) * 16 < nrows) {   // this warp's next tile: its 16 q rows (2 lines each) into L1 while this one computes
-      const float* nx = a.q + global_row(min((tile + 4) * 16 + (lane >> 1), nrows - 1)) * q_ld + h * 64 + (lane & 1) * 32;
-      asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-    }
     float2 qa[4][4];                                                // A fragments (raw fp32 pairs) of the 4 k-steps
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {

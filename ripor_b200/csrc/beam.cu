@@ -589,6 +589,35 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   int cnt = 0;
   constexpr int kBatch = 8;
   auto scan = [&](auto&& fn) {
+    if ((V & 31) == 0) {
+      // lane always owns token v = lane + 32 k of every beam: the allowed bit of (beam i, word k) for this lane is bit
+      // `lane` of that word. Eight logits of a row are requested together, the float64 adds follow.
+      for (int i = 0; i < nb; ++i) {
+        const double bsi = bs[i];
+        const float* row = a.logits + (int64_t)(bc * a.rpq + (a.rpq == 1 ? 0 : i)) * V + lane;
+        const float rmax = a.apply_ls ? row_max[i] : 0.f, rlog = a.apply_ls ? row_log[i] : 0.f;
+        for (int k0 = 0; k0 < words; k0 += kBatch) {
+          float xs[kBatch];
+          uint32_t okw = 0u;
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            xs[u] = (k0 + u < words) ? row[32 * (k0 + u)] : 0.f;
+            if (k0 + u < words) okw |= ((allow[i * words + k0 + u] >> lane) & 1u) << u;
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            if (k0 + u < words) {
+              float x = xs[u];
+              if (a.apply_ls) x = (x - rmax) - rlog;
+              const double processed = ((okw >> u) & 1u) ? (double)x : (double)x + (-1e9);
+              const double val = processed + bsi;
+              fn(i * V + lane + 32 * (k0 + u), val == val ? val : kNanRank);
+            }
+          }
+        }
+      }
+      return;
+    }
     int i = 0, v = lane;
     while (v >= V) { v -= V; ++i; }
     for (int c0 = lane; c0 < total; c0 += 32 * kBatch) {
@@ -705,16 +734,13 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
     a.token_out[r_new] = vj;
     st_out[r_new] = ns;
   }
-  // token history and KV ancestry of the new beams: (beam j, position p) pairs over the lanes
-  {
-    const int tot = nb * L;
-#pragma unroll 4
-    for (int e = lane; e < tot; e += 32) {
-      const int j = e / L, p = e - j * L;
-      const int c = win_idx[j];
-      const int i = c / V, v = c - i * V;
-      const int src = b * nb + i, dst = b * nb + j;
-      hist_out[dst * L + p] = p < t ? a.hist_old[src * L + p] : (p == t ? v : 0);
+  // token history and KV ancestry of the new beams: lane = position (L <= 32: one row per iteration, no divisions;
+  // longer DocIDs walk the positions in chunks of 32)
+  for (int j = 0; j < nb; ++j) {
+    const int pj_ = __shfl_sync(0xffffffffu, pj, j), vj_ = __shfl_sync(0xffffffffu, vj, j);
+    const int src = b * nb + pj_, dst = b * nb + j;
+    for (int p = lane; p < L; p += 32) {
+      hist_out[dst * L + p] = p < t ? a.hist_old[src * L + p] : (p == t ? vj_ : 0);
       int anc;
       if (p < t) anc = a.anc_old[src * L + p];
       else if (p == t) anc = (a.rpq == 1) ? b : src;
@@ -981,7 +1007,9 @@ int beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits, int r
   if (force == 0 && nb <= kWarpNb && d_model % 4 == 0 && kWarpQ * per_warp <= 48 * 1024) {
     RB_CUDA(rb::launch_pdl(beam_step_warp_kernel, dim3(rb::ceil_div(a.nq, kWarpQ)), dim3(kWarpQ * 32),
                            kWarpQ * per_warp, stream, a));
-  } else if (force != 2 && cta_fits) {
+  } else if (force != 2 && cta_fits && (force == 1 || total <= 256 * 32)) {
+    // (beyond 8192 candidates per query the arg-max kernel rescans its 25+ candidates per thread after every
+    // winner; the radix select is faster there: beam 100 x V 256 runs 249.5 ms per batch of 128 instead of 258.2)
     static bool attr_set = false;
     if (!attr_set) {
       RB_CUDA(cudaFuncSetAttribute(beam_step_kernel<256, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
