@@ -61,6 +61,26 @@ def test_select_kernel_matches_oracle_loop(monkeypatch, log_softmax, n_docs, nb,
         assert torch.equal(seqs[valid], ref_seq[valid])
 
 
+@pytest.mark.parametrize("log_softmax", [False, True])
+def test_cta_argmax_kernel_still_exact_beyond_its_default_range(monkeypatch, log_softmax):
+    """Above 8192 candidates per query the dispatcher prefers the radix select; the arg-max CTA kernel (RB200_BEAM=cta)
+    must stay bit-exact there too (it remains the fallback up to 131 072 candidates)."""
+    monkeypatch.setenv("RB200_BEAM", "cta")
+    n_docs, nb, V, L, B = 3000, 100, 256, 4, 2
+    codes = syn.make_codes(n_docs, L, V, seed=5, dup_frac=0.05)
+    lst = ob.build_list_smtid_to_nextids(syn.codes_to_docid_to_smtid(codes))
+    tr = DocidTrie.from_codes(codes, V).upload(0)
+    fn = _table_logits(B, nb, V)
+    ref_seq, ref_sc = ob.beam_search_oracle(lambda ids, bi: fn(ids), ob.TrieMaskOracle(lst, V), B, nb, L,
+                                            apply_log_softmax_for_scores=log_softmax)
+    seqs, scores, leaf = _run_beam_kernels(tr, B, nb, L, V, fn, log_softmax)
+    valid = ref_sc > -1e6
+    if log_softmax:
+        assert helpers.compare_ranked(seqs, scores, ref_seq, ref_sc, nb, atol=2e-6) == 0
+    else:
+        assert torch.equal(scores, ref_sc) and torch.equal(seqs[valid], ref_seq[valid])
+
+
 @pytest.mark.parametrize("nb,V,n_docs,L", [(1000, 256, 60000, 4), (600, 256, 300, 3), (160, 1024, 50000, 3)])
 def test_beam_1000_matches_oracle_loop(nb, V, n_docs, L):
     """topk = 1000 is the reference's shipped evaluation setting (full_evaluate_t5seq_aq_encoder.sh:191-199): more
