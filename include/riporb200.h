@@ -84,8 +84,10 @@ int rb200_trie_mask_host(const rb200_trie* trie, const int64_t* input_ids_host, 
 int rb200_trie_leaf_docs(const rb200_trie* trie, int64_t leaf, const int64_t** docs_host, int64_t* n);
 /* exact-match lookup of a full code row; *leaf = -1 if absent. code_host has L entries (int32). */
 int rb200_trie_find_leaf(const rb200_trie* trie, const int32_t* code_host, int64_t* leaf);
-/* copy the tables to HBM of `device` (idempotent; one device per handle: one process per GPU, as the reference
- * runs, evaluate.py:463-470). */
+/* copy the tables to HBM of `device` (idempotent per device; a handle may be uploaded to several devices - the
+ * reference runs one process per GPU, evaluate.py:463-470, a single-process caller uploads once per device). The
+ * device entry points below use the copy on the calling thread's current device (mask, leaf expansion) or on the
+ * beam state's / engine's device. */
 int rb200_trie_upload(rb200_trie* trie, int device);
 /* Device form of the smtid -> docids mapping (evaluate.py:118-128, 439-446): leaf_ranges_dev int32 [n, 2] as
  * returned by rb200_beam_finalize / rb200_engine_search; docs_dev int64 [n, max_docs_per_row] receives the input rows

@@ -981,7 +981,7 @@ int beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits, int r
     return 0;
   }
   StepArgs a;
-  a.tv = trie->device_view();
+  a.tv = trie->device_view(bm->device);
   a.t = bm->step; a.nb = bm->nb; a.rpq = rows_per_query; a.apply_ls = apply_log_softmax; a.L = bm->L;
   a.d_model = d_model;
   a.nq = bm->n_active;
@@ -1062,7 +1062,7 @@ int launch_tail_prepare(rb200_beam* bm, const rb200_trie* trie, const TailLayout
   const int rows = bm->n_frozen * bm->nb;
   if (rows == 0) return 0;
   const bool from_hist = trie == nullptr;
-  tail_prepare_kernel<<<rows, 128, 0, s>>>(from_hist ? TrieView{} : trie->device_view(), lay, bm->nb, bm->L, d_model,
+  tail_prepare_kernel<<<rows, 128, 0, s>>>(from_hist ? TrieView{} : trie->device_view(bm->device), lay, bm->nb, bm->L, d_model,
                                            from_hist ? 1 : 0, bm->fz_list, bm->qstate, bm->fz_state, bm->fz_hist,
                                            in_tabs_dev, start_emb, x);
   RB_CUDA(cudaGetLastError());
@@ -1186,14 +1186,14 @@ int rb200_beam_reset_beams(rb200_beam* bm, const rb200_trie* trie, int batch, in
   RB_REQUIRE(batch >= 1 && batch <= bm->max_batch, "batch %d outside [1, %d]", batch, bm->max_batch);
   RB_REQUIRE(num_beams >= 1 && num_beams <= bm->max_nb, "num_beams %d outside [1, %d]", num_beams, bm->max_nb);
   RB_REQUIRE(trie->V == bm->V, "trie V=%d but beam state was created for V=%d", trie->V, bm->V);
-  if (trie->device != bm->device)
-    return rb::fail(RB200_ERR_STATE, "trie is on device %d, beam state on device %d: call rb200_trie_upload",
-                    trie->device, bm->device);
+  if (trie->tables_on(bm->device) == nullptr)
+    return rb::fail(RB200_ERR_STATE, "the trie has not been uploaded to device %d (beam state): call rb200_trie_upload",
+                    bm->device);
   bm->batch = batch; bm->nb = num_beams; bm->step = 0; bm->cur = 0;
   bm->n_active = batch; bm->n_frozen = 0; bm->compacted = false;
   const int R = batch * bm->nb;
   beam_reset_kernel<<<rb::ceil_div(R, 128), 128, 0, (cudaStream_t)stream>>>(
-      trie->device_view(), bm->nb, bm->L, batch, bm->scores[0], bm->state[0], bm->hist[0], bm->anc[0], bm->qstate,
+      trie->device_view(bm->device), bm->nb, bm->L, batch, bm->scores[0], bm->state[0], bm->hist[0], bm->anc[0], bm->qstate,
       bm->qlist, bm->counts);
   RB_CUDA(cudaGetLastError());
   rb::launch_count()++;

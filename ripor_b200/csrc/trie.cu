@@ -27,14 +27,16 @@ rb::TrieView rb200_trie::host_view() const {
   return v;
 }
 
-rb::TrieView rb200_trie::device_view() const {
+rb::TrieView rb200_trie::device_view(int d) const {
   TrieView v;
-  if (code_bytes == 1) v.codes8 = static_cast<const uint8_t*>(d_codes);
-  else v.codes16 = static_cast<const uint16_t*>(d_codes);
-  v.node_bitmap = d_node_bitmap;
-  v.node_child_ptr = d_node_child_ptr;
-  v.child_lo = d_child_lo;
-  v.child_node = d_child_node;
+  const DevTables* t = tables_on(d);
+  if (t == nullptr) return v;
+  if (code_bytes == 1) v.codes8 = static_cast<const uint8_t*>(t->codes);
+  else v.codes16 = static_cast<const uint16_t*>(t->codes);
+  v.node_bitmap = t->node_bitmap;
+  v.node_child_ptr = t->node_child_ptr;
+  v.child_lo = t->child_lo;
+  v.child_node = t->child_node;
   v.L = L; v.V = V; v.words = words; v.U = (int32_t)U; v.root_node = root_node;
   return v;
 }
@@ -248,11 +250,15 @@ int rb200_trie_build(const void* codes_host, int code_bytes, int64_t n_docs, int
 
 int rb200_trie_free(rb200_trie* tr) {
   if (!tr) return 0;
-  if (tr->device >= 0) {
-    cudaFree(tr->d_codes); cudaFree(tr->d_node_bitmap); cudaFree(tr->d_node_child_ptr);
-    cudaFree(tr->d_child_lo); cudaFree(tr->d_child_node);
-    cudaFree(tr->d_leaf_ptr); cudaFree(tr->d_leaf_docs);
+  int prev = 0;
+  const bool have_dev = !tr->dev.empty() && cudaGetDevice(&prev) == cudaSuccess;
+  for (auto& t : tr->dev) {
+    cudaSetDevice(t.device);
+    cudaFree(t.codes); cudaFree(t.node_bitmap); cudaFree(t.node_child_ptr);
+    cudaFree(t.child_lo); cudaFree(t.child_node);
+    cudaFree(t.leaf_ptr); cudaFree(t.leaf_docs);
   }
+  if (have_dev) cudaSetDevice(prev);
   delete tr;
   return 0;
 }
@@ -353,21 +359,34 @@ int rb200_trie_find_leaf(const rb200_trie* tr, const int32_t* code, int64_t* lea
 
 int rb200_trie_upload(rb200_trie* tr, int device) {
   RB_REQUIRE(tr, "null argument");
-  if (tr->device == device) return 0;
-  RB_REQUIRE(tr->device < 0, "trie already uploaded to device %d", tr->device);
+  if (tr->tables_on(device) != nullptr) {
+    tr->device = device;
+    return 0;
+  }
+  int ndev = 0;
+  RB_CUDA(cudaGetDeviceCount(&ndev));
+  RB_REQUIRE(device >= 0 && device < ndev, "device %d not present (%d devices)", device, ndev);
   int prev = 0;
   RB_CUDA(cudaGetDevice(&prev));
   RB_CUDA(cudaSetDevice(device));
+  rb200_trie::DevTables t;
+  t.device = device;
   auto up = [&](void** dst, const void* src, size_t bytes) -> cudaError_t {
     cudaError_t e = cudaMalloc(dst, bytes ? bytes : 4);
     if (e != cudaSuccess) return e;
     return cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice);
   };
-  RB_CUDA(up(&tr->d_codes, tr->codes.data(), tr->codes.size()));
-  RB_CUDA(up((void**)&tr->d_node_bitmap, tr->node_bitmap.data(), 4 * tr->node_bitmap.size()));
-  RB_CUDA(up((void**)&tr->d_node_child_ptr, tr->node_child_ptr.data(), 4 * tr->node_child_ptr.size()));
-  RB_CUDA(up((void**)&tr->d_child_lo, tr->child_lo.data(), 4 * tr->child_lo.size()));
-  RB_CUDA(up((void**)&tr->d_child_node, tr->child_node.data(), 4 * tr->child_node.size()));
+  cudaError_t err = up(&t.codes, tr->codes.data(), tr->codes.size());
+  if (err == cudaSuccess) err = up((void**)&t.node_bitmap, tr->node_bitmap.data(), 4 * tr->node_bitmap.size());
+  if (err == cudaSuccess) err = up((void**)&t.node_child_ptr, tr->node_child_ptr.data(), 4 * tr->node_child_ptr.size());
+  if (err == cudaSuccess) err = up((void**)&t.child_lo, tr->child_lo.data(), 4 * tr->child_lo.size());
+  if (err == cudaSuccess) err = up((void**)&t.child_node, tr->child_node.data(), 4 * tr->child_node.size());
+  if (err != cudaSuccess) {           // give back the partial copy
+    cudaFree(t.codes); cudaFree(t.node_bitmap); cudaFree(t.node_child_ptr); cudaFree(t.child_lo); cudaFree(t.child_node);
+    cudaSetDevice(prev);
+    return rb::fail(RB200_ERR_CUDA, "rb200_trie_upload to device %d: %s", device, cudaGetErrorString(err));
+  }
+  tr->dev.push_back(t);
   tr->device = device;
   RB_CUDA(cudaSetDevice(prev));
   return 0;
@@ -377,23 +396,24 @@ int rb200_trie_leaf_expand(rb200_trie* tr, const int32_t* leaf_ranges, int64_t n
                            void* stream) {
   RB_REQUIRE(tr && leaf_ranges && docs && counts, "null argument");
   RB_REQUIRE(k >= 1 && k <= 4096, "max_docs_per_row=%d outside [1, 4096]", k);
-  if (tr->device < 0) return rb::fail(RB200_ERR_STATE, "trie not uploaded: call rb200_trie_upload first");
+  if (tr->dev.empty()) return rb::fail(RB200_ERR_STATE, "trie not uploaded: call rb200_trie_upload first");
+  int cur = 0;
+  RB_CUDA(cudaGetDevice(&cur));                    // the buffers belong to the calling thread's current device
+  rb200_trie::DevTables* t = tr->tables_on(cur);
+  if (t == nullptr)
+    return rb::fail(RB200_ERR_STATE, "trie not uploaded to device %d: call rb200_trie_upload first", cur);
   if (n == 0) return 0;
-  if (tr->d_leaf_ptr == nullptr) {                 // first use: the leaf -> documents CSR goes to HBM as int32
+  if (t->leaf_ptr == nullptr) {                    // first use: the leaf -> documents CSR goes to HBM as int32
     RB_REQUIRE(tr->n_docs < 0x7fffffff, "too many documents for the device leaf table");
     std::vector<int32_t> p32(tr->leaf_ptr.begin(), tr->leaf_ptr.end()), d32(tr->leaf_docs.begin(), tr->leaf_docs.end());
-    int prev = 0;
-    RB_CUDA(cudaGetDevice(&prev));
-    RB_CUDA(cudaSetDevice(tr->device));
-    RB_CUDA(cudaMalloc((void**)&tr->d_leaf_ptr, p32.size() * 4));
-    RB_CUDA(cudaMalloc((void**)&tr->d_leaf_docs, d32.size() * 4 + 4));
-    RB_CUDA(cudaMemcpy(tr->d_leaf_ptr, p32.data(), p32.size() * 4, cudaMemcpyHostToDevice));
-    RB_CUDA(cudaMemcpy(tr->d_leaf_docs, d32.data(), d32.size() * 4, cudaMemcpyHostToDevice));
-    RB_CUDA(cudaSetDevice(prev));
+    RB_CUDA(cudaMalloc((void**)&t->leaf_ptr, p32.size() * 4));
+    RB_CUDA(cudaMalloc((void**)&t->leaf_docs, d32.size() * 4 + 4));
+    RB_CUDA(cudaMemcpy(t->leaf_ptr, p32.data(), p32.size() * 4, cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(t->leaf_docs, d32.data(), d32.size() * 4, cudaMemcpyHostToDevice));
   }
   const int warps = 4;
   leaf_expand_kernel<<<rb::ceil_div(n, warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      tr->d_leaf_ptr, tr->d_leaf_docs, leaf_ranges, n, k, docs, counts);
+      t->leaf_ptr, t->leaf_docs, leaf_ranges, n, k, docs, counts);
   RB_CUDA(cudaGetLastError());
   rb::launch_count()++;
   return 0;
@@ -401,12 +421,16 @@ int rb200_trie_leaf_expand(rb200_trie* tr, const int32_t* leaf_ranges, int64_t n
 
 int rb200_trie_mask_device(const rb200_trie* tr, const int64_t* ids, int64_t R, int T, double* mask, void* stream) {
   RB_REQUIRE(tr && ids && mask, "null argument");
-  if (tr->device < 0) return rb::fail(RB200_ERR_STATE, "trie not uploaded: call rb200_trie_upload first");
+  if (tr->dev.empty()) return rb::fail(RB200_ERR_STATE, "trie not uploaded: call rb200_trie_upload first");
+  int cur = 0;
+  RB_CUDA(cudaGetDevice(&cur));
+  if (tr->tables_on(cur) == nullptr)
+    return rb::fail(RB200_ERR_STATE, "trie not uploaded to device %d: call rb200_trie_upload first", cur);
   RB_REQUIRE(T >= 1 && T <= tr->L, "prefix length T=%d outside [1, L=%d]", T, tr->L);
   if (R == 0) return 0;
   const int warps = 4;
   trie_mask_kernel<<<rb::ceil_div(R, warps), warps * 32, warps * tr->words * 4, (cudaStream_t)stream>>>(
-      tr->device_view(), ids, R, T, mask);
+      tr->device_view(cur), ids, R, T, mask);
   RB_CUDA(cudaGetLastError());
   rb::launch_count()++;
   return 0;

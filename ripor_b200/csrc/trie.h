@@ -106,17 +106,32 @@ struct rb200_trie {
   std::vector<int64_t> leaf_docs;      // [n_docs] input row indices grouped by leaf, input order inside
   std::vector<int64_t> level_counts;   // [L]
   int32_t root_node = -1;
-  // device copies
+  // device copies: one set of tables per device the trie was uploaded to (a single-process multi-GPU caller uploads
+  // the same handle to every device; `device` is the most recent one, reported by rb200_trie_get_info)
+  struct DevTables {
+    int device = -1;
+    void* codes = nullptr;
+    uint32_t* node_bitmap = nullptr;
+    int32_t* node_child_ptr = nullptr;
+    int32_t* child_lo = nullptr;
+    int32_t* child_node = nullptr;
+    int32_t* leaf_ptr = nullptr;       // [U+1] (rb200_trie_leaf_expand; uploaded on first use)
+    int32_t* leaf_docs = nullptr;      // [n_docs]
+  };
+  std::vector<DevTables> dev;
   int device = -1;
-  void* d_codes = nullptr;
-  uint32_t* d_node_bitmap = nullptr;
-  int32_t* d_node_child_ptr = nullptr;
-  int32_t* d_child_lo = nullptr;
-  int32_t* d_child_node = nullptr;
-  int32_t* d_leaf_ptr = nullptr;       // [U+1] (rb200_trie_leaf_expand; uploaded on first use)
-  int32_t* d_leaf_docs = nullptr;      // [n_docs]
 
+  const DevTables* tables_on(int d) const {
+    for (const auto& t : dev)
+      if (t.device == d) return &t;
+    return nullptr;
+  }
+  DevTables* tables_on(int d) {
+    for (auto& t : dev)
+      if (t.device == d) return &t;
+    return nullptr;
+  }
   rb::TrieView host_view() const;
-  rb::TrieView device_view() const;
+  rb::TrieView device_view(int d) const;      // tables of device d (must have been uploaded there)
   int64_t table_bytes() const;
 };

@@ -196,9 +196,10 @@ class DocidTrie:
         R, T = ids.shape
         if ids.is_cuda:
             out = torch.empty((R, self.V), dtype=torch.float64, device=ids.device)
-            self.upload(ids.device.index or 0)
-            _lib.check(_lib.lib().rb200_trie_mask_device(self._h, ids.data_ptr(), R, T, out.data_ptr(),
-                                                         _lib.stream_ptr()))
+            with torch.cuda.device(ids.device):          # the C ABI uses the tables of the current device
+                self.upload(torch.cuda.current_device())
+                _lib.check(_lib.lib().rb200_trie_mask_device(self._h, ids.data_ptr(), R, T, out.data_ptr(),
+                                                             _lib.stream_ptr()))
             return out
         out = torch.empty((R, self.V), dtype=torch.float64)
         _lib.check(_lib.lib().rb200_trie_mask_host(self._h, ids.data_ptr(), R, T, out.data_ptr()))
@@ -213,9 +214,10 @@ class DocidTrie:
         n = lr.shape[0]
         docs = torch.empty((n, max_docs_per_row), dtype=torch.int64, device=lr.device)
         counts = torch.empty((n,), dtype=torch.int32, device=lr.device)
-        self.upload(lr.device.index or 0)
-        _lib.check(_lib.lib().rb200_trie_leaf_expand(self._h, lr.data_ptr(), n, max_docs_per_row, docs.data_ptr(),
-                                                     counts.data_ptr(), _lib.stream_ptr()))
+        with torch.cuda.device(lr.device):               # the C ABI uses the tables of the current device
+            self.upload(torch.cuda.current_device())
+            _lib.check(_lib.lib().rb200_trie_leaf_expand(self._h, lr.data_ptr(), n, max_docs_per_row, docs.data_ptr(),
+                                                         counts.data_ptr(), _lib.stream_ptr()))
         return docs, counts
 
     def docid_of_row(self, row: int) -> str:

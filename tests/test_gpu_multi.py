@@ -57,3 +57,37 @@ def test_cli_gather_over_nccl_equals_single_process_run(tmp_path):
             assert list(run[q]) == list(ref[q]), (mode, q)                # same documents in the same rank order
             for d in ref[q]:
                 assert abs(run[q][d] - ref[q][d]) < 1e-4
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_one_trie_handle_serves_two_devices():
+    """A single-process multi-GPU caller uploads one trie handle to every device: masks,
+    searches and leaf expansions on cuda:1 use cuda:1's copy of the tables."""
+    import numpy as np
+    from ripor_b200 import synthetic as syn
+    from ripor_b200.generation import PrefixConstrainLogitProcessorFastSparse, generate_for_constrained_prefix_beam_search
+    from ripor_b200.modeling import T5SeqAQEncoder
+    from ripor_b200.trie import DocidTrie
+    from tests import helpers
+    L, nb, B = 8, 5, 4
+    dims = syn.T5Dims.tiny(docid_len=L)
+    w = syn.make_weights(dims)
+    V = dims.decoder_vocab_size
+    codes = syn.make_codes(3000, L, V, dup_frac=0.05)
+    ids, mask = syn.make_queries(B, S=14, vocab_size=dims.vocab_size)
+    ref_seq, ref_sc, _, _ = helpers.oracle_cached_search(w, dims, codes, ids, mask, nb, L)
+    trie = DocidTrie.from_codes(codes, V)
+    proc = PrefixConstrainLogitProcessorFastSparse.from_trie(trie)
+    pre = torch.from_numpy(np.concatenate([np.zeros((6, 1), np.int64), codes[:6, :3].astype(np.int64)], 1))
+    host_mask = trie.mask(pre)
+    for dev in ("cuda:0", "cuda:1", "cuda:0"):
+        assert torch.equal(trie.mask(pre.to(dev)).cpu(), host_mask)
+        model = T5SeqAQEncoder.from_weights(dims, w).to(dev)
+        out = generate_for_constrained_prefix_beam_search(
+            model.base_model, proc, input_ids=ids.to(dev), attention_mask=mask.to(dev), max_new_tokens=L, num_beams=nb,
+            num_return_sequences=nb, output_scores=True, return_dict_in_generate=True, precision="tf32x3")
+        assert out.sequences.device == torch.device(dev)
+        assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0
+        docs, counts = trie.expand_ranges(out.leaf_ranges, 4)
+        lo, hi = out.leaf_ranges[0].tolist()
+        assert docs[0, : int(counts[0])].tolist() == trie.rows_for_range(lo, hi).tolist()
