@@ -64,9 +64,31 @@ def test_config2_exact_size_64_queries(kind):
     assert sum(hist) == B                         # at 8.8 M documents every query is frozen well before step 32
     if kind == "zipf":
         assert sum(1 for n in hist if n > 0) >= 3, hist      # ... at different steps on the skewed trie
-    # every ranked DocID is a full code of the collection: exactly one leaf, and the leaf holds >= 1 document
+    # size-independent properties over ALL 256 queries (the oracle covers the first 64):
+    # every ranked DocID is a full code of the collection (exactly one leaf) and re-spells through the host trie walk,
     leaf = out.leaf_ranges.cpu()
     assert torch.all(leaf[:, 1] - leaf[:, 0] == 1)
+    trie = DocidTrie.from_codes(codes, V)
+    all_seqs = out.sequences.cpu()
+    for r in range(0, B * nb, 97):
+        assert trie.find_leaf(all_seqs[r, 1:].tolist()) == int(leaf[r, 0])
+    # scores are finite and non-increasing within a query, the nb DocIDs of a query are distinct, column 0 is the
+    # decoder start id,
+    sc = out.sequences_scores.view(B, nb).cpu()
+    assert torch.isfinite(sc).all() and torch.all(sc[:, :-1] >= sc[:, 1:])
+    assert torch.all(all_seqs[:, 0] == 0)
+    per_q = all_seqs.view(B, nb, L + 1)
+    assert all(len({tuple(row) for row in per_q[b].tolist()}) == nb for b in range(B))
+    # and the search is idempotent: the same batch again gives the same bits (no state leaks between calls)
+    again = _engine_search(model, trie, ids, mask, nb, L, precision="auto")
+    assert torch.equal(again.sequences, out.sequences) and torch.equal(again.sequences_scores, out.sequences_scores)
+    # the device-side leaf expansion returns the rows whose codes spell the ranked DocIDs (1 % of the rows are duplicates)
+    docs, counts = trie.expand_ranges(out.leaf_ranges, 8)
+    docs, counts = docs.cpu().numpy(), counts.cpu().numpy()
+    assert counts.min() >= 1
+    for r in range(0, B * nb, 211):
+        rows = docs[r, : counts[r]]
+        assert np.all(codes[rows] == all_seqs[r, 1:].numpy())
 
 
 def test_config3_beam100_t5base_dims():
