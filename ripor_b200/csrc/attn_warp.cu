@@ -1123,81 +1123,6 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(Ta
   pdl_trigger();
 }
 
-// Warp-pair variant (planes only): the two warps of a pair share ONE set of K/V planes and take one 16-query tile
-// each. Half the shared memory per warp -> 16 warps per SM at 128 registers (the single-warp kernel is held at 12 by
-// its 18.4 KB of planes per warp), and a task's two tiles run side by side instead of one after the other. Staging is
-// split between the two warps by position parity; named barriers (one per pair) hand the planes over.
-constexpr int kPairWarps = 4;                               // 2 pairs per CTA
-__device__ __forceinline__ void pair_sync(int pair) { asm volatile("bar.sync %0, 64;" ::"r"(pair + 1) : "memory"); }
-
-__global__ void __launch_bounds__(kPairWarps * 32, 4) self_attn_tail_mma16_pair_kernel(TailAttnArgs a, ActOut ctx) {
-  extern __shared__ __align__(16) unsigned char tmsmem[];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pair = warp >> 1, wp = warp & 1;               // wp: this warp's tile, and its share of the staging
-  const int half = lane >> 4, l16 = lane & 15;
-  __half* k_hi = reinterpret_cast<__half*>(tmsmem + pair * kTailMmaWarpBytes);
-  __half* k_lo = k_hi + 32 * kKLd;
-  __half* v_hi = k_lo + 32 * kKLd;
-  __half* v_lo = v_hi + 32 * kKLd;
-  const int inner = a.H * 64, L = a.L;
-  const int P = a.lay.P;
-  const int ntask = a.R * a.H;
-  bool bad = false;
-  for (int e = wp * 32 + lane; e < (32 - P) * 8; e += 64) {   // rows >= P: zero, once
-    const int p = P + (e >> 3), ch = e & 7;
-    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
-    *reinterpret_cast<uint4*>(k_hi + p * kKLd + ch * 8) = z;
-    *reinterpret_cast<uint4*>(k_lo + p * kKLd + ch * 8) = z;
-    *reinterpret_cast<uint4*>(v_hi + p * kKLd + ch * 8) = z;
-    *reinterpret_cast<uint4*>(v_lo + p * kKLd + ch * 8) = z;
-  }
-  const int pl = lane >> 3, ch = lane & 7;
-  __half* dst_plane = (pl == 0 ? k_hi : (pl == 1 ? k_lo : (pl == 2 ? v_hi : v_lo))) + ch * 8;
-  pdl_wait();
-  const int pairs_per_cta = kPairWarps / 2;
-  for (int wid = blockIdx.x * pairs_per_cta + pair; wid < ntask; wid += gridDim.x * pairs_per_cta) {
-    const int rp = wid / a.H, h = wid - rp * a.H;
-    const int bq = a.fz_list[rp / a.nb];
-    const int r = bq * a.nb + rp % a.nb;
-    const int t = a.qstart ? a.qstart[bq] : 0, T = P - t;
-    // this warp's Q tile does not depend on the planes: request it first
-    uint32_t qh[4][4], ql[4][4];
-    const bool has_tile = wp * 16 < T;
-    if (has_tile) tail_load_q_planes(a, rp, h, t, T, wp, qh, ql);
-    pair_sync(pair);                                          // the previous task's fragment reads are done (both warps)
-    {
-      const __half* src = a.qkv_hi + ((pl & 1) ? a.qkv_plane : 0) + ((pl >> 1) ? 2 * inner : inner) + h * 64 + ch * 8;
-      for (int p = t + wp; p < P; p += 2)
-        cp_async16_any(dst_plane + p * kKLd, src + ((int64_t)a.lay.off[p] + rp) * 3 * inner);
-      asm volatile("cp.async.commit_group;" ::: "memory");
-    }
-    // cached prefix (fp32): iterations alternate between the two warps
-    const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
-    for (int it = wp; 2 * it < t; it += 2) {
-      const int p = 2 * it + half;
-      const int slot = __shfl_sync(0xffffffffu, slot_l, p);
-      if (p < t) {
-        const float4 kk = *reinterpret_cast<const float4*>(a.cache_k + (int64_t)slot * inner + h * 64 + l16 * 4);
-        const float4 vv = *reinterpret_cast<const float4*>(a.cache_v + (int64_t)slot * inner + h * 64 + l16 * 4);
-        uint32_t h0, l0, h1, l1;
-        split_h2(kk.x, kk.y, h0, l0, bad);
-        split_h2(kk.z, kk.w, h1, l1, bad);
-        *reinterpret_cast<uint2*>(k_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(k_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
-        split_h2(vv.x, vv.y, h0, l0, bad);
-        split_h2(vv.z, vv.w, h1, l1, bad);
-        *reinterpret_cast<uint2*>(v_hi + p * kKLd + l16 * 4) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(v_lo + p * kKLd + l16 * 4) = make_uint2(l0, l1);
-      }
-    }
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    pair_sync(pair);                                          // both halves of the planes are in place
-    if (has_tile) tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, wp, qh, ql);
-  }
-  if (bad && ctx.overflow) *ctx.overflow = 1;
-  pdl_trigger();
-}
-
 }  // namespace
 
 bool launch_self_attn_warp(const SelfAttnArgs& a, ActOut ctx, cudaStream_t s, int* status) {
@@ -1289,24 +1214,6 @@ int launch_self_attn_tail(const TailAttnArgs& a, ActOut ctx, cudaStream_t s) {
     attr_set = true;
   }
   RB_REQUIRE(a.qkv_hi == nullptr || mma, "q | k | v planes are only read by the tensor-core tail kernel");
-  {
-    const char* pe = getenv("RB200_SELF_TAIL");            // pair | single: force a variant (A/B measurements)
-    const bool want_pair = pe ? strcmp(pe, "pair") == 0 : false;
-    if (mma && a.qkv_hi != nullptr && want_pair) {
-      static bool pair_attr = false;
-      if (!pair_attr) {
-        RB_CUDA(cudaFuncSetAttribute(self_attn_tail_mma16_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (kPairWarps / 2) * kTailMmaWarpBytes));
-        pair_attr = true;
-      }
-      const int want = ceil_div((int64_t)a.R * a.H, kPairWarps / 2);
-      const dim3 pgrid(want < 4 * sms ? want : 4 * sms), pblock(kPairWarps * 32);
-      RB_CUDA(launch_pdl(self_attn_tail_mma16_pair_kernel, pgrid, pblock, (size_t)(kPairWarps / 2) * kTailMmaWarpBytes, s,
-                         a, ctx));
-      launch_count()++;
-      return 0;
-    }
-  }
   const size_t smem = mma ? (size_t)kWarps * kTailMmaWarpBytes : (size_t)kWarps * kTailWarpFloats * sizeof(float);
   const int want = ceil_div((int64_t)a.R * a.H, kWarps);
   const int per_sm = mma ? 3 : 2;
