@@ -1020,21 +1020,24 @@ __device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const Ac
                                                  const __half* k_lo, const __half* v_hi, const __half* v_lo, int rp,
                                                  int h, int t, int T, bool& bad) {
   uint32_t qh[4][4], ql[4][4];
-  if (a.qkv_hi == nullptr) {
-    for (int tile = 0; tile * 16 < T; ++tile) {
-      tail_load_q_f32(a, rp, h, t, T, tile, qh, ql, bad);
-      tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, tile, qh, ql);
+  const bool qplanes = a.qkv_hi != nullptr;
+  uint32_t qhn[4][4], qln[4][4];
+  if (qplanes) tail_load_q_planes(a, rp, h, t, T, 0, qh, ql);
+  else tail_load_q_f32(a, rp, h, t, T, 0, qh, ql, bad);
+#pragma unroll 1
+  for (int tile = 0; tile * 16 < T; ++tile) {
+    const bool more = (tile + 1) * 16 < T;
+    if (more) {
+      if (qplanes) tail_load_q_planes(a, rp, h, t, T, tile + 1, qhn, qln);
+      else tail_load_q_f32(a, rp, h, t, T, tile + 1, qhn, qln, bad);
     }
-    return;
-  }
-  tail_load_q_planes(a, rp, h, t, T, 0, qh, ql);
-  if (T > 16) {                               // at most two tiles (P <= 32)
-    uint32_t qh1[4][4], ql1[4][4];
-    tail_load_q_planes(a, rp, h, t, T, 1, qh1, ql1);
-    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, 0, qh, ql);
-    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, 1, qh1, ql1);
-  } else {
-    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, 0, qh, ql);
+    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, tile, qh, ql);
+    if (more) {
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { qh[kk][u] = qhn[kk][u]; ql[kk][u] = qln[kk][u]; }
+    }
   }
 }
 
@@ -1089,7 +1092,7 @@ __global__ void __launch_bounds__(kWarps * 32, 3) self_attn_tail_mma16_kernel(Ta
     // ---- positions that arrive as fp32 (the cached prefix; everything when there are no planes): split here -------
     const int nconv = planes ? t : P;
     const int slot_l = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)r * L + lane] : -1;
-#pragma unroll 4
+#pragma unroll 2
     for (int it = 0; it < 16; ++it) {
       if (2 * it >= nconv) break;                                   // warp-uniform
       const int p = 2 * it + half;
