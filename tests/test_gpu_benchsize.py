@@ -172,3 +172,32 @@ def test_shipped_training_data_launch_prefix_search():
     r = 7
     rows = trie.rows_for_range(int(leaf[r, 0]), int(leaf[r, 1]))
     assert len(rows) >= 1 and np.all(codes[rows][:, :L] == out.sequences[r, 1:].cpu().numpy())
+
+
+@pytest.mark.parametrize("kind", ["uniform", "zipf"])
+def test_t5base_variants_log_softmax_long_source_fewer_returns(kind):
+    """The remaining switches of the path together at t5-base dimensions over the 8.8 M-doc tries: log-softmax scores
+    (apply_log_softmax_for_scores, evaluate.py:123-126), shared input/output codebook tables and d^-1/2 scaling
+    (t5_generative_retriever.py:254-258,427-428), a padded source length beyond one 32-key attention chunk (S = 48: the
+    ragged tail's multi-chunk cross-attention), and num_return_sequences < num_beams."""
+    B, nb, keep, L, V = 12, 10, 3, 32, 256
+    dims = syn.T5Dims.t5_base(docid_len=L, shared_output_input_embeds=True, scaleup_output_hidden=True)
+    w = syn.make_weights(dims)
+    codes = _codes(kind)
+    ids, mask = syn.make_queries(B, S=48, seed=906)
+    with torch.no_grad():
+        enc = t5_math.encoder_forward(w, dims, ids, mask)
+        dec = t5_math.CachedDecoder(w, dims, enc, mask, nb)
+
+        def step(dec_ids, bi):
+            if bi is not None:
+                dec.reorder(bi)
+            return dec.step(None if dec_ids.shape[1] == 1 else dec_ids[:, -1])
+        ref_seq, ref_sc = ob.beam_search_oracle(step, SortedCodesMask(codes, V), B, nb, L, num_return_sequences=keep,
+                                                apply_log_softmax_for_scores=True)
+    model = T5SeqAQEncoder.from_weights(dims, w)
+    out = _engine_search(model, DocidTrie.from_codes(codes, V), ids, mask, nb, L, log_softmax=True, keep=keep,
+                         precision="auto")
+    assert out.sequences.shape == (B * keep, L + 1)
+    assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, keep, atol=1e-3) == 0
+    assert sum(out.frozen_at_step) == B
