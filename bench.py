@@ -58,7 +58,7 @@ def parse_args():
     ap.add_argument("--no-zipf", action="store_true", help="skip the sibling measurement on the skewed trie")
     ap.add_argument("--zipf", action="store_true", help="run the skewed-trie sibling under torchrun too")
     ap.add_argument("--no-configs", action="store_true", help="skip the BASELINE configs 3/4/5 + topk=1000 block")
-    ap.add_argument("--configs-only", default="", help="comma list out of c3,c4,c5,top1000,rank4x100 (default: all)")
+    ap.add_argument("--configs-only", default="", help="comma list out of c3,c4,c5,top1000,top1000x8,rank4x100 (default: all)")
     return ap.parse_args()
 
 
@@ -467,10 +467,10 @@ def run_ours(a):
                 zres["parity"] = check_parity(zout, B, nb, L, w, dims, SortedCodesMask(zcodes, a.codebook), zids, zmask, zq)
             result["zipf"] = zres
         del zcodes, ztrie, zproc, zout
-    # ---- the other BASELINE configs + the reference's shipped launch, bounded (2 steps each) ----
+    # ---- the other BASELINE configs + the reference's shipped launch, bounded (2 steps each; 8 for the millisecond-long launches) ----
     if not a.no_configs and a.trie == "uniform" and (a.model, nb, L, a.codebook) == ("t5-base", 10, 32, 256):
         want = [c for c in a.configs_only.split(",") if c] or \
-            (["c3"] if world > 1 else ["c3", "top1000", "rank4x100", "c4", "c5"])
+            (["c3"] if world > 1 else ["top1000", "rank4x100", "top1000x8", "c3", "c4", "c5"])
         result["configs"] = run_configs(a, want, model, w, dims, measure, rank, world)
     if rank == 0:
         print(json.dumps(result), flush=True)
@@ -481,7 +481,7 @@ def run_ours(a):
 
 def run_configs(a, want, base_model, base_w, base_dims, measure, rank, world):
     """q/s (+ a small parity check on rank 0) for BASELINE configs[2..4] and the reference's shipped evaluation launch
-    (full_scripts/full_evaluate_t5seq_aq_encoder.sh:191-199: batch 1, topk 1000). 2 timed steps each."""
+    (full_scripts/full_evaluate_t5seq_aq_encoder.sh:191-199: batch 1, topk 1000). 2 timed steps each (8 for the millisecond-long launches)."""
     import torch
     from oracle.range_mask import SortedCodesMask
     from ripor_b200 import synthetic as syn
@@ -498,6 +498,9 @@ def run_configs(a, want, base_model, base_w, base_dims, measure, rank, world):
                    nb=10, B=256, pq=4),
         "top1000": dict(name="reference's shipped eval launch: t5-base, batch_size=1, topk=1000, L=32", model="t5-base",
                         L=32, V=256, nb=1000, B=1, pq=0),
+        # the same launch with --batch_size 8 (what a user of this engine would pass: one SM-filling batch)
+        "top1000x8": dict(name="shipped eval launch at --batch_size 8: t5-base, topk=1000, L=32", model="t5-base",
+                          L=32, V=256, nb=1000, B=8, pq=0),
         # full_scripts/full_evaluate_t5seq_aq_encoder.sh:128-139: t5seq_aq_get_qid_to_smtid_rankdata, DocID prefixes
         "rank4x100": dict(name="reference's shipped training-data launch: t5-base, batch_size=4, topk=100, "
                                "max_new_token=16 (prefix search over the 32-code trie)", model="t5-base", L=16, trie_L=32,
@@ -522,8 +525,11 @@ def run_configs(a, want, base_model, base_w, base_dims, measure, rank, world):
                 dims = dims_for(c["model"], tk[0], c["V"])
                 w = syn.make_weights(dims)
                 model = T5SeqAQEncoder.from_weights(dims, w).to(dev)
-            res, o, ids, mask = measure(model, proc, c["B"], c["nb"], c["L"], a.src_len, 2, 1, a.precision, seed_off=1000)
-            res.update({"workload": c["name"], "unit": "queries/s", "steps": 2, "warmup": 1})
+            # the small launches are milliseconds long: more warm-up and steps, so that the power state the previous
+            # (heavy) config left behind does not colour them
+            st, wu = (8, 8) if c["B"] * c["nb"] <= 1000 else (2, 1)
+            res, o, ids, mask = measure(model, proc, c["B"], c["nb"], c["L"], a.src_len, st, wu, a.precision, seed_off=1000)
+            res.update({"workload": c["name"], "unit": "queries/s", "steps": st, "warmup": wu})
             if rank == 0 and c["pq"] > 0:
                 res["parity"] = check_parity(o, c["B"], c["nb"], c["L"], w, dims, SortedCodesMask(codes, c["V"]), ids, mask,
                                              c["pq"])

@@ -572,7 +572,8 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma_kernel(CrossAttnArgs a,
   auto global_row = [&](int q) {
     return (a.ragged ? (int64_t)a.lay.off[t0 + q / rpq] : (int64_t)(q / rpq) * a.block_rows) + (int64_t)b * rpq + (q % rpq);
   };
-  for (int tile = warp; tile * 16 < nrows; tile += 4) {
+  // gridDim.y CTAs share one (query, head): each restages the <= 32 keys and takes every gridDim.y-th group of 4 tiles
+  for (int tile = blockIdx.y * 4 + warp; tile * 16 < nrows; tile += 4 * gridDim.y) {
     const int q0 = tile * 16 + g, q1 = q0 + 8;                      // this lane's two rows of the tile
     const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64;
     const float* qr1 = a.q + global_row(min(q1, nrows - 1)) * q_ld + h * 64;
@@ -756,7 +757,8 @@ __global__ void __launch_bounds__(128, MINB) cross_attn_mma16_kernel(CrossAttnAr
   const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
   const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
   const int vrow = (lane & 7) + 8 * ((lane >> 3) & 1), vcol = 8 * (lane >> 4);   // ldmatrix row of this lane
-  for (int tile = warp; tile * 16 < nrows; tile += 4) {
+  // gridDim.y CTAs share one (query, head): each restages the <= 32 keys and takes every gridDim.y-th group of 4 tiles
+  for (int tile = blockIdx.y * 4 + warp; tile * 16 < nrows; tile += 4 * gridDim.y) {
     const int q0 = tile * 16 + g, q1 = q0 + 8;
     const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64 + 2 * t;
     const float* qr1 = a.q + global_row(min(q1, nrows - 1)) * q_ld + h * 64 + 2 * t;
@@ -1242,10 +1244,24 @@ bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, 
     // selects the round-1 build
     const char* oe = getenv("RB200_XATTN_OCC");
     const int occ = oe ? atoi(oe) : 4;
+    // few (query, head) pairs with many rows each (the shipped --batch_size 1 --topk 1000 launch: 12 pairs of up to
+    // 32 000 rows): split each pair's 64-row tile groups over gridDim.y CTAs until the grid fills the SMs 4 deep
+    static const int sms = []() {
+      int dev = 0, n = 148;
+      if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+      return n;
+    }();
+    const int64_t max_rows = (int64_t)(a.ragged ? a.lay.P : a.nblocks) * a.rows_per_query;
+    const int groups = (int)ceil_div(max_rows, (int64_t)64);
+    int split = (int)ceil_div((int64_t)4 * sms, (int64_t)B * a.H);
+    split = split < 1 ? 1 : (split > groups ? groups : split);
+    const char* se = getenv("RB200_XATTN_SPLIT");
+    if (se && atoi(se) > 0) split = atoi(se) > groups ? groups : atoi(se);
+    const dim3 grid(B * a.H, split);
     const cudaError_t err = prec_is_fp16(ctx.mode)
-                                ? (occ == 3 ? launch_pdl(cross_attn_mma16_kernel<3>, dim3(B * a.H), dim3(128), 0, s, a, ctx)
-                                            : launch_pdl(cross_attn_mma16_kernel<4>, dim3(B * a.H), dim3(128), 0, s, a, ctx))
-                                : launch_pdl(cross_attn_mma_kernel, dim3(B * a.H), dim3(128), 0, s, a, ctx);
+                                ? (occ == 3 ? launch_pdl(cross_attn_mma16_kernel<3>, grid, dim3(128), 0, s, a, ctx)
+                                            : launch_pdl(cross_attn_mma16_kernel<4>, grid, dim3(128), 0, s, a, ctx))
+                                : launch_pdl(cross_attn_mma_kernel, grid, dim3(128), 0, s, a, ctx);
     *status = err == cudaSuccess ? 0 : fail(RB200_ERR_CUDA, "cross_attn_mma_kernel launch: %s", cudaGetErrorString(err));
     launch_count()++;
     return true;

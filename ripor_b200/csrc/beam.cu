@@ -339,6 +339,14 @@ __device__ __forceinline__ double key_f64(unsigned long long k) {
   return __longlong_as_double((long long)b);
 }
 
+// histogram increment, aggregated over the lanes of the warp that hit the same bin: the first digit of the value
+// select (sign + exponent) and the tie cut put hundreds of thousands of candidates into a handful of bins, and
+// same-address shared-memory atomics serialise
+__device__ __forceinline__ void hist_add(uint32_t* hist, unsigned bin) {
+  const unsigned peers = __match_any_sync(__activemask(), bin);
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&hist[bin], (uint32_t)__popc(peers));
+}
+
 __global__ void __launch_bounds__(kSelThreads) beam_step_select_kernel(const StepArgs a, int pbuf) {
   const int bc = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nb = a.nb, V = a.tv.V, words = a.tv.words;
@@ -432,7 +440,7 @@ __global__ void __launch_bounds__(kSelThreads) beam_step_select_kernel(const Ste
     const int shift = 64 - bits_done - dbits;
     for_each_cand([&](int, unsigned long long key) {
       if (bits_done == 0 || (key >> (64 - bits_done)) == prefix)
-        atomicAdd(&hist[(unsigned)((key >> shift) & ((1u << dbits) - 1u))], 1u);
+        hist_add(hist, (unsigned)((key >> shift) & ((1u << dbits) - 1u)));
     });
     __syncthreads();
     const int D = pick_digit(true);
@@ -453,7 +461,7 @@ __global__ void __launch_bounds__(kSelThreads) beam_step_select_kernel(const Ste
       for (int k = tid; k < kSelBins; k += kSelThreads) hist[k] = 0u;
       __syncthreads();
       for_each_cand([&](int c, unsigned long long key) {
-        if (key == prefix && (pass == 0 || (c >> 12) == idx_hi)) atomicAdd(&hist[pass == 0 ? (c >> 12) : (c & 4095)], 1u);
+        if (key == prefix && (pass == 0 || (c >> 12) == idx_hi)) hist_add(hist, pass == 0 ? (c >> 12) : (c & 4095));
       });
       __syncthreads();
       const int D = pick_digit(false);
@@ -894,7 +902,6 @@ __global__ void tail_finish_kernel(rb::TailLayout lay, int nb, int L, int V, con
   double* val = s + nb;                                // [nb]
   int* perm = reinterpret_cast<int*>(val + nb);        // [nb] frozen beam index in slot j
   int* nperm = perm + nb;                              // [nb]
-  int* tok = nperm + nb;                               // [nb] forced token of the beam in slot j at this step
   const int fq = blockIdx.x;
   const int b = fz_list[fq];
   const int t0 = qstate[b];
@@ -904,15 +911,17 @@ __global__ void tail_finish_kernel(rb::TailLayout lay, int nb, int L, int V, con
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
       const double v = (double)picked[lay.off[p] + fq * nb + perm[j]] + s[j];
       val[j] = v == v ? v : kNanRank;
-      tok[j] = hist_fz[(b * nb + perm[j]) * L + p];
     }
     __syncthreads();
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
       const double mine = val[j];
-      const int cj = j * V + tok[j];
+      // candidates ahead of slot j's under (value desc, flat index asc); flat index = slot * V + token with
+      // token < V, so among equal values exactly the lower slots go first
       int rank = 0;
-      for (int k = 0; k < nb; ++k)          // slots differ, so the flat indices k * V + token differ: a total order
-        rank += cand_better(val[k], k * V + tok[k], mine, cj);
+#pragma unroll 4
+      for (int k = 0; k < j; ++k) rank += val[k] >= mine;
+#pragma unroll 4
+      for (int k = j + 1; k < nb; ++k) rank += val[k] > mine;
       s[rank] = mine;          // s[] is not read in this phase
       nperm[rank] = perm[j];
     }
@@ -1087,10 +1096,10 @@ int launch_tail_finish(rb200_beam* bm, const rb200_trie* trie, const TailLayout&
   threads = threads > 1024 ? 1024 : threads;
   static bool attr_set = false;
   if (!attr_set) {
-    RB_CUDA(cudaFuncSetAttribute(tail_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelMaxNb * 28));
+    RB_CUDA(cudaFuncSetAttribute(tail_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelMaxNb * 24));
     attr_set = true;
   }
-  tail_finish_kernel<<<nfz, threads, (size_t)nb * 28, s>>>(lay, nb, bm->L, bm->V, bm->fz_list, bm->qstate, picked,
+  tail_finish_kernel<<<nfz, threads, (size_t)nb * 24, s>>>(lay, nb, bm->L, bm->V, bm->fz_list, bm->qstate, picked,
                                                           bm->fz_scores, bm->fz_state, bm->fz_hist, bm->scores[c],
                                                           bm->state[c], bm->hist[c]);
   RB_CUDA(cudaGetLastError());

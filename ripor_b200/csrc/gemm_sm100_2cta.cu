@@ -333,11 +333,20 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     // ===== epilogue: warp -> (TMEM lane quarter q = warp % 4, column half ch); lane = row of the quarter =====
     const int q = warp & 3, ch = (warp - 2) >> 2;
     uint8_t* tile_s = epi_smem + (warp - 2) * kEpiTile;
-    constexpr int HALF = BN / 2;
+    // 64-wide tiles (the latency-bound GEMMs of small batches): the 16-bit plane epilogues work on 64 columns at a
+    // time, so one warp per lane quarter takes the whole width and its column-half partner only keeps the barrier
+    // protocol going
+    constexpr int HALF = BN >= 128 ? BN / 2 : BN;
+    const bool epi_active = BN >= 128 || ch == 0;
     bool bad = false;                                  // fp16 planes: a value left the representable range
     int lt = 0;
     for (int tile = cluster_id; tile < num_tiles; tile += num_clusters, ++lt) {
       const int buf = lt & 1;
+      if (!epi_active) {
+        mbar_wait(&tmem_full_bar[buf], (lt >> 1) & 1);
+        if (lane == 0) mbar_arrive_leader(&tmem_empty_bar[buf]);
+        continue;
+      }
       const int row0 = ((tile / num_n_tiles) * 2 + (int)rank) * BM + q * 32;
       const int col0 = (tile % num_n_tiles) * BN + ch * HALF;
       // ---- everything that does not need the accumulator happens while the MMAs are still running ----
@@ -623,6 +632,12 @@ int launch_bn2(const GemmArgs& g, cudaStream_t s) {
     return e ? atoi(e) : 0;
   }();
   const bool wide = force ? force == 256 : (cost256 <= cost128 || tiles256 >= 4 * (int64_t)sm_pairs);
+  // Small batches (few hundred rows: the reference's shipped --batch_size 1 / 4 launches): every tile has an SM pair
+  // to itself and the launch lasts as long as ONE tile's K loop, which 128-wide tiles run at the shared-memory
+  // operand bandwidth (0.55 us per 64-deep k-block). 64-wide tiles halve the MMA work per k-block; taken only while
+  // all of them still fit one round.
+  const bool narrow = force ? force == 64 : m_pairs * ceil_div(g.N, 64) <= sm_pairs;
+  if (narrow) return launch_cfg2<ELEM_BYTES, NTERMS, 64>(g, s);
   if (g.N >= 256 && wide) return launch_cfg2<ELEM_BYTES, NTERMS, 256>(g, s);
   return launch_cfg2<ELEM_BYTES, NTERMS, 128>(g, s);
 }

@@ -142,6 +142,7 @@ GEMM_TOL = {"fp32": 2e-6, "tf32x3": 3e-5, "fp16x3": 3e-5, "bf16x3": 6e-5, "tf32"
 @pytest.mark.parametrize("mode", ["fp32", "tf32x3", "fp16x3", "bf16x3", "tf32", "bf16"])
 @pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 256, 128), (2560, 2304, 768), (77, 16, 128), (40, 768, 3072),
                                    (300, 3072, 768), (1, 256, 768),
+                                   (400, 2304, 768), (1000, 768, 768),   # 64-wide tiles: one round of tiles, small batches
                                    (40000, 512, 64)])    # many tiles per SM pair: the 256-wide tile path of the tail
 def test_gemm_modes_against_float64(mode, M, N, K):
     g = torch.Generator().manual_seed(M * 7 + N * 3 + K)
