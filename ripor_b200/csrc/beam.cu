@@ -519,6 +519,11 @@ __global__ void __launch_bounds__(kSelThreads) beam_step_select_kernel(const Ste
 constexpr int kWarpNb = 16;          // beams per query this kernel handles
 constexpr int kWarpQ = 4;            // queries (warps) per CTA
 constexpr int kListLd = kWarpNb + 1; // padded per-lane list stride
+// per warp: list values [32][kListLd] f64 | list indices [32][kListLd] i32 | bs[kWarpNb] f64 | win_val[kWarpNb] f64 |
+//           win_idx[kWarpNb] | row_max, row_log, thr_ok, thr_pen [kWarpNb] f32 | allow[kWarpNb * words]
+__host__ __device__ constexpr size_t warp_step_smem(int words) {
+  return (32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4 + 4 + 4) + (size_t)kWarpNb * words * 4 + 15) & ~(size_t)15;
+}
 
 __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -530,10 +535,7 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   const int b = a.qlist ? a.qlist[bc] : bc;
 
   extern __shared__ __align__(16) unsigned char wsmem_raw[];
-  // per warp: list values [32][kListLd] f64 | list indices [32][kListLd] i32 | bs[kWarpNb] f64 | win_val[kWarpNb] f64 |
-  //           win_idx[kWarpNb] | row_max, row_log [kWarpNb] f32 | allow[kWarpNb * words]
-  const size_t per_warp = 32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4) + (size_t)kWarpNb * words * 4;
-  unsigned char* base = wsmem_raw + warp * ((per_warp + 15) & ~(size_t)15);
+  unsigned char* base = wsmem_raw + warp * warp_step_smem(words);
   double* list_v = reinterpret_cast<double*>(base);
   double* bs = list_v + 32 * kListLd;
   double* win_val = bs + kWarpNb;
@@ -541,7 +543,9 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   int* win_idx = list_c + 32 * kListLd;
   float* row_max = reinterpret_cast<float*>(win_idx + kWarpNb);
   float* row_log = row_max + kWarpNb;
-  uint32_t* allow = reinterpret_cast<uint32_t*>(row_log + kWarpNb);
+  float* thr_ok = row_log + kWarpNb;
+  float* thr_pen = thr_ok + kWarpNb;
+  uint32_t* allow = reinterpret_cast<uint32_t*>(thr_pen + kWarpNb);
 
   // ---- A. allowed-children bitmaps, beam scores, optional log-softmax statistics ---------------------------------
   // The trie tables are far larger than L2 (codes: 280 MB at 8.8 M documents), so every lookup is a DRAM round trip:
@@ -588,44 +592,40 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
 
   // ---- B1. every lane: sorted list of its best candidates ------------------------------------------------------------
   // Two passes over the lane's candidates (flat index c = i * V + v = lane + 32 k, walked without divisions; logits
-  // requested kBatch at a time). Pass 1 only tracks the lane's best value; the nb-th largest of the 32 lane maxima is
-  // a lower bound tau of the query's nb-th best candidate (they are nb real candidates). Pass 2 inserts only
-  // candidates >= tau into the lane's sorted list, so the data-dependent insertion - which a warp pays at the depth
-  // of its slowest lane - runs for a few dozen candidates per query instead of for all nb * V of them.
+  // requested kBatch at a time). Pass 1 finds a value of a real candidate per lane (its best); the nb-th largest of
+  // these 32 values is a lower bound tau of the query's nb-th best candidate. Pass 2 inserts only candidates >= tau
+  // into the lane's sorted list, so the data-dependent insertion - which a warp pays at the depth of its slowest lane
+  // - runs for a few dozen candidates per query instead of for all nb * V of them.
+  // V % 32 == 0 (every shipped codebook): lane owns token lane + 32 k of every beam and both passes stay in fp32 for
+  // all but the surviving candidates. x -> value(x) = ((double)x [+ -1e9]) + beam score is non-decreasing in x inside
+  // a (beam, allowed / penalised) class, so pass 1 needs one float64 evaluation per class (on the lane's largest x of
+  // the class: the value of a real candidate), and pass 2 compares x with a per-class fp32 threshold rounded so that
+  // x < threshold PROVES value(x) < tau (margin 2^-48 relative, far above the 2^-53 rounding of the three float64
+  // operations; NaN / infinite thresholds fail the comparison and send the candidate to the exact evaluation).
   double* lv = list_v + lane * kListLd;
   int* lc = list_c + lane * kListLd;
   int cnt = 0;
   constexpr int kBatch = 8;
-  auto scan = [&](auto&& fn) {
-    if ((V & 31) == 0) {
-      // lane always owns token v = lane + 32 k of every beam: the allowed bit of (beam i, word k) for this lane is bit
-      // `lane` of that word. Eight logits of a row are requested together, the float64 adds follow.
-      for (int i = 0; i < nb; ++i) {
-        const double bsi = bs[i];
-        const float* row = a.logits + (int64_t)(bc * a.rpq + (a.rpq == 1 ? 0 : i)) * V + lane;
-        const float rmax = a.apply_ls ? row_max[i] : 0.f, rlog = a.apply_ls ? row_log[i] : 0.f;
-        for (int k0 = 0; k0 < words; k0 += kBatch) {
-          float xs[kBatch];
-          uint32_t okw = 0u;
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            xs[u] = (k0 + u < words) ? row[32 * (k0 + u)] : 0.f;
-            if (k0 + u < words) okw |= ((allow[i * words + k0 + u] >> lane) & 1u) << u;
-          }
-#pragma unroll
-          for (int u = 0; u < kBatch; ++u) {
-            if (k0 + u < words) {
-              float x = xs[u];
-              if (a.apply_ls) x = (x - rmax) - rlog;
-              const double processed = ((okw >> u) & 1u) ? (double)x : (double)x + (-1e9);
-              const double val = processed + bsi;
-              fn(i * V + lane + 32 * (k0 + u), val == val ? val : kNanRank);
-            }
-          }
-        }
+  const bool lane_tokens = (V & 31) == 0;
+  auto exact_value = [&](float x, bool ok, double bsi) {
+    const double processed = ok ? (double)x : (double)x + (-1e9);
+    const double val = processed + bsi;
+    return val == val ? val : kNanRank;
+  };
+  auto insert = [&](int c, double val) {
+    if (cnt < nb || cand_better(val, c, lv[cnt - 1], lc[cnt - 1])) {
+      int pos = cnt < nb ? cnt : nb - 1;                              // a full list drops its last entry
+      while (pos > 0 && cand_better(val, c, lv[pos - 1], lc[pos - 1])) {
+        lv[pos] = lv[pos - 1];
+        lc[pos] = lc[pos - 1];
+        --pos;
       }
-      return;
+      lv[pos] = val;
+      lc[pos] = c;
+      if (cnt < nb) ++cnt;
     }
+  };
+  auto scan = [&](auto&& fn) {     // generic walk (V not a multiple of 32): float64 value of every candidate
     int i = 0, v = lane;
     while (v >= V) { v -= V; ++i; }
     for (int c0 = lane; c0 < total; c0 += 32 * kBatch) {
@@ -648,8 +648,42 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   double tau = -INFINITY;
   if (total > 32 * nb) {                       // (with few candidates per lane the filter saves nothing)
     double mine = -INFINITY;
-    scan([&](int, double val) { mine = val > mine ? val : mine; });
-    for (int j = 0; j < nb; ++j) {             // nb-th largest of the lane maxima: nb arg-max rounds with removal
+    if (lane_tokens) {
+      for (int i = 0; i < nb; ++i) {
+        const float* row = a.logits + (int64_t)(bc * a.rpq + (a.rpq == 1 ? 0 : i)) * V + lane;
+        const float rmax = a.apply_ls ? row_max[i] : 0.f, rlog = a.apply_ls ? row_log[i] : 0.f;
+        float m_ok = -INFINITY, m_pen = -INFINITY;        // fmaxf drops NaNs: the maxima stay values of real candidates
+        for (int k0 = 0; k0 < words; k0 += kBatch) {
+          float xs[kBatch];
+          uint32_t aw[kBatch];
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            xs[u] = (k0 + u < words) ? row[32 * (k0 + u)] : -INFINITY;
+            aw[u] = (k0 + u < words) ? allow[i * words + k0 + u] : 0u;
+          }
+#pragma unroll
+          for (int u = 0; u < kBatch; ++u) {
+            float x = xs[u];
+            if (a.apply_ls) x = (x - rmax) - rlog;
+            const bool ok = (aw[u] >> lane) & 1u;
+            m_ok = ok ? fmaxf(m_ok, x) : m_ok;
+            m_pen = ok ? m_pen : fmaxf(m_pen, x);
+          }
+        }
+        const double bsi = bs[i];
+        if (m_ok > -INFINITY) {
+          const double val = exact_value(m_ok, true, bsi);
+          mine = val > mine ? val : mine;
+        }
+        if (m_pen > -INFINITY) {
+          const double val = exact_value(m_pen, false, bsi);
+          mine = val > mine ? val : mine;
+        }
+      }
+    } else {
+      scan([&](int, double val) { mine = val > mine ? val : mine; });
+    }
+    for (int j = 0; j < nb; ++j) {             // nb-th largest of the lane values: nb arg-max rounds with removal
       double m = mine;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
@@ -661,19 +695,53 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
       if (lane == __ffs(owners) - 1) mine = -INFINITY;        // remove ONE holder of the maximum
     }
   }
-  scan([&](int c, double val) {
-    if (val >= tau && (cnt < nb || cand_better(val, c, lv[cnt - 1], lc[cnt - 1]))) {
-      int pos = cnt < nb ? cnt : nb - 1;                              // a full list drops its last entry
-      while (pos > 0 && cand_better(val, c, lv[pos - 1], lc[pos - 1])) {
-        lv[pos] = lv[pos - 1];
-        lc[pos] = lc[pos - 1];
-        --pos;
-      }
-      lv[pos] = val;
-      lc[pos] = c;
-      if (cnt < nb) ++cnt;
+  if (lane_tokens) {
+    if (lane < nb) {                           // lane i: the two thresholds of beam i
+      const double bsi = bs[lane];
+      const double dlt = tau - bsi;
+      const double mag = fabs(tau) + fabs(bsi);
+      thr_ok[lane] = __double2float_rd(dlt - mag * 0x1p-48);
+      thr_pen[lane] = __double2float_rd((dlt + 1e9) - (mag + 1e9) * 0x1p-47);
     }
-  });
+    __syncwarp();
+    for (int i = 0; i < nb; ++i) {
+      const float* row = a.logits + (int64_t)(bc * a.rpq + (a.rpq == 1 ? 0 : i)) * V + lane;
+      const float rmax = a.apply_ls ? row_max[i] : 0.f, rlog = a.apply_ls ? row_log[i] : 0.f;
+      const float t_ok = thr_ok[i], t_pen = thr_pen[i];
+      for (int k0 = 0; k0 < words; k0 += kBatch) {
+        float xs[kBatch];
+        uint32_t aw[kBatch];
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          xs[u] = (k0 + u < words) ? row[32 * (k0 + u)] : 0.f;
+          aw[u] = (k0 + u < words) ? allow[i * words + k0 + u] : 0u;
+        }
+        uint32_t surv = 0u;                    // candidates the fp32 comparison could not rule out
+#pragma unroll
+        for (int u = 0; u < kBatch; ++u) {
+          float x = xs[u];
+          if (a.apply_ls) x = (x - rmax) - rlog;
+          const bool ok = (aw[u] >> lane) & 1u;
+          if (k0 + u < words && !(x < (ok ? t_ok : t_pen))) surv |= 1u << u;
+        }
+        if (surv != 0u) {
+          const double bsi = bs[i];
+          while (surv != 0u) {
+            const int k = k0 + __ffs(surv) - 1;
+            surv &= surv - 1u;
+            float x = row[32 * k];
+            if (a.apply_ls) x = (x - rmax) - rlog;
+            const double val = exact_value(x, (allow[i * words + k] >> lane) & 1u, bsi);
+            if (val >= tau) insert(i * V + lane + 32 * k, val);
+          }
+        }
+      }
+    }
+  } else {
+    scan([&](int c, double val) {
+      if (val >= tau) insert(c, val);
+    });
+  }
   // ---- B2. nb rounds of warp arg-max over the list heads ---------------------------------------------------------
   int hd = 0;
   for (int j = 0; j < nb; ++j) {
@@ -1008,8 +1076,7 @@ int beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits, int r
   const int64_t total = (int64_t)nb * bm->V;
   const char* fe = getenv("RB200_BEAM");       // cta | select: force one formulation (parity tests); read per call
   const int force = !fe ? 0 : (strcmp(fe, "cta") == 0 ? 1 : (strcmp(fe, "select") == 0 ? 2 : 0));
-  const size_t per_warp = (32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4) + (size_t)kWarpNb * a.tv.words * 4 + 15) &
-                          ~(size_t)15;
+  const size_t per_warp = warp_step_smem(a.tv.words);
   const size_t smem = cta_smem_bytes(nb, a.tv.words);
   const bool cta_fits = total <= 1024 * kMaxPerThread && smem <= 200 * 1024;
   // (very wide codebooks would push the per-warp bitmaps past the default 48 KB of dynamic shared memory)

@@ -81,6 +81,58 @@ def test_cta_argmax_kernel_still_exact_beyond_its_default_range(monkeypatch, log
         assert torch.equal(scores, ref_sc) and torch.equal(seqs[valid], ref_seq[valid])
 
 
+def _adversarial_logits(kind, B, nb, V, seed):
+    """Logit tables that stress the fp32 pre-filter of the warp beam kernel: its thresholds must never drop a candidate
+    the float64 ranking would keep."""
+    g = torch.Generator().manual_seed(seed)
+    t = torch.randn(B * nb, 97, V, generator=g)
+    if kind == "ties":            # a handful of distinct values: most candidates tie exactly at the cut
+        t = torch.round(t * 1.5)
+    elif kind == "huge":          # |logit| ~ 1e9: penalised and allowed candidates interleave
+        t = t * 7e8
+    elif kind == "tiny":          # values far below the float64 spacing of the accumulated beam scores
+        t = t * 1e-30
+    elif kind == "mixed_scale":   # every row on its own scale, 1e-6 .. 1e6 (below the penalty: the oracle loop applies)
+        t = t * (10.0 ** torch.randint(-6, 7, (B * nb, 97, 1), generator=g).float())
+    elif kind == "nonfinite":     # NaN ranks last, infinities are ordinary extreme values
+        r = torch.rand(B * nb, 97, V, generator=g)
+        t = torch.where(r < 0.02, torch.full_like(t, float("nan")), t)
+        t = torch.where((r >= 0.02) & (r < 0.03), torch.full_like(t, float("inf")), t)
+        t = torch.where((r >= 0.03) & (r < 0.05), torch.full_like(t, float("-inf")), t)
+    elif kind == "constant":      # everything ties
+        t = torch.zeros_like(t) + 0.25
+
+    def fn(ids):
+        h = (ids * torch.arange(1, ids.shape[1] + 1)).sum(1) % 97
+        rows = torch.arange(ids.shape[0]) // nb * nb if ids.shape[1] == 1 else torch.arange(ids.shape[0])
+        return t[rows, h]
+    return fn
+
+
+@pytest.mark.parametrize("log_softmax", [False, True])
+@pytest.mark.parametrize("kind", ["ties", "huge", "tiny", "mixed_scale", "nonfinite", "constant"])
+@pytest.mark.parametrize("n_docs,nb,V,L,B", [(5000, 10, 256, 6, 7), (40, 16, 256, 5, 5), (3000, 7, 1024, 4, 3),
+                                             (2000, 10, 64, 5, 4)])
+def test_warp_kernel_prefilter_is_exact_on_adversarial_logits(monkeypatch, log_softmax, kind, n_docs, nb, V, L, B):
+    """The warp kernel rules most candidates out with an fp32 comparison against per-beam thresholds; the CTA arg-max
+    kernel evaluates every candidate in float64. Same inputs -> the same beams, bit for bit (sequences, float64-exact
+    scores, leaf ranges), also with ties at the cut, |logits| around the 1e9 penalty, NaN / inf logits and small tries
+    whose beams carry the penalty."""
+    codes = syn.make_codes(n_docs, L, V, seed=9, dup_frac=0.05)
+    tr = DocidTrie.from_codes(codes, V).upload(0)
+    fn = _adversarial_logits(kind, B, nb, V, seed=21)
+    got = _run_beam_kernels(tr, B, nb, L, V, fn, log_softmax)                # default dispatch: the warp kernel
+    monkeypatch.setenv("RB200_BEAM", "cta")
+    want = _run_beam_kernels(tr, B, nb, L, V, fn, log_softmax)
+    assert torch.equal(got[0], want[0])
+    assert torch.equal(got[1].view(torch.int32), want[1].view(torch.int32))  # bit pattern: NaN-safe equality
+    assert torch.equal(got[2], want[2])
+    if kind == "mixed_scale" and not log_softmax:                            # finite, untied logits: also the oracle loop
+        lst = ob.build_list_smtid_to_nextids(syn.codes_to_docid_to_smtid(codes))
+        ref_seq, ref_sc = ob.beam_search_oracle(lambda ids, bi: fn(ids), ob.TrieMaskOracle(lst, V), B, nb, L)
+        assert torch.equal(got[1], ref_sc)
+
+
 @pytest.mark.parametrize("nb,V,n_docs,L", [(1000, 256, 60000, 4), (600, 256, 300, 3), (160, 1024, 50000, 3)])
 def test_beam_1000_matches_oracle_loop(nb, V, n_docs, L):
     """topk = 1000 is the reference's shipped evaluation setting (full_evaluate_t5seq_aq_encoder.sh:191-199): more
