@@ -39,6 +39,15 @@ __device__ __forceinline__ bool cand_better(double va, int ia, double vb, int ib
   return va > vb || (va == vb && ia < ib);
 }
 
+__device__ __forceinline__ unsigned long long f64_key(double v) {   // ascending order-preserving (-0.0 == +0.0)
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v + 0.0);
+  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double key_f64(unsigned long long k) {
+  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+  return __longlong_as_double((long long)b);
+}
+
 struct StepArgs {
   TrieView tv;
   int t, nb, rpq, apply_ls, L, d_model;
@@ -330,14 +339,6 @@ constexpr int kSelBins = 4096;
 constexpr int kSelMaxNb = 2048;
 constexpr int kSelMaxSmem = 226 * 1024;   // dynamic part; the kernel also has a few hundred bytes of static shared memory
 
-__device__ __forceinline__ unsigned long long f64_key(double v) {   // ascending order-preserving
-  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
-  return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
-}
-__device__ __forceinline__ double key_f64(unsigned long long k) {
-  const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
-  return __longlong_as_double((long long)b);
-}
 
 // histogram increment, aggregated over the lanes of the warp that hit the same bin: the first digit of the value
 // select (sign + exponent) and the tie cut put hundreds of thousands of candidates into a handful of bins, and
@@ -525,10 +526,12 @@ __host__ __device__ constexpr size_t warp_step_smem(int words) {
   return (32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4 + 4 + 4) + (size_t)kWarpNb * words * 4 + 15) & ~(size_t)15;
 }
 
+template <int WORDS>   // codebook words known at compile time (8: V = 256, 32: V = 1024), 0 = read from the trie view
 __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepArgs a) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bc = blockIdx.x * kWarpQ + warp;
-  const int nb = a.nb, V = a.tv.V, words = a.tv.words, t = a.t, L = a.L;
+  const int words = WORDS ? WORDS : a.tv.words, V = WORDS ? 32 * WORDS : a.tv.V;
+  const int nb = a.nb, t = a.t, L = a.L;
   const int total = nb * V;
   rb::pdl_wait();
   if (bc >= a.nq) return;
@@ -606,7 +609,7 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   int* lc = list_c + lane * kListLd;
   int cnt = 0;
   constexpr int kBatch = 8;
-  const bool lane_tokens = (V & 31) == 0;
+  const bool lane_tokens = WORDS ? true : (V & 31) == 0;
   auto exact_value = [&](float x, bool ok, double bsi) {
     const double processed = ok ? (double)x : (double)x + (-1e9);
     const double val = processed + bsi;
@@ -683,17 +686,19 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
     } else {
       scan([&](int, double val) { mine = val > mine ? val : mine; });
     }
-    for (int j = 0; j < nb; ++j) {             // nb-th largest of the lane values: nb arg-max rounds with removal
-      double m = mine;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        const double om = __shfl_xor_sync(0xffffffffu, m, o);
-        m = om > m ? om : m;
-      }
-      tau = m;
-      const unsigned owners = __ballot_sync(0xffffffffu, mine == m);
-      if (lane == __ffs(owners) - 1) mine = -INFINITY;        // remove ONE holder of the maximum
+    // nb-th largest of the lane values: nb warp-max rounds with removal, on order-preserving 64-bit keys (two 32-bit
+    // redux.sync per round instead of five float64 shuffle + compare steps)
+    unsigned long long key = f64_key(mine);
+    unsigned long long tkey = 0ull;
+    for (int j = 0; j < nb; ++j) {
+      const unsigned mh = __reduce_max_sync(0xffffffffu, (unsigned)(key >> 32));
+      const bool top = (unsigned)(key >> 32) == mh;
+      const unsigned ml = __reduce_max_sync(0xffffffffu, top ? (unsigned)key : 0u);
+      tkey = ((unsigned long long)mh << 32) | ml;
+      const unsigned owners = __ballot_sync(0xffffffffu, key == tkey);
+      if (lane == __ffs(owners) - 1) key = 0ull;               // remove ONE holder of the maximum (0 < every real key)
     }
+    tau = tkey == 0ull ? -INFINITY : key_f64(tkey);            // (fewer than nb lanes held a candidate: no filter)
   }
   if (lane_tokens) {
     if (lane < nb) {                           // lane i: the two thresholds of beam i
@@ -743,18 +748,23 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
     });
   }
   // ---- B2. nb rounds of warp arg-max over the list heads ---------------------------------------------------------
+  // (value desc, flat index asc) on keys: warp max of the high word, of the low word among its holders, then the
+  // smallest flat index among the holders of the full key
   int hd = 0;
   for (int j = 0; j < nb; ++j) {
-    double v = hd < cnt ? lv[hd] : -INFINITY;
-    int c = hd < cnt ? lc[hd] : INT_MAX;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
-      const int oc = __shfl_xor_sync(0xffffffffu, c, o);
-      if (cand_better(ov, oc, v, c)) { v = ov; c = oc; }
+    const unsigned long long key = hd < cnt ? f64_key(lv[hd]) : 0ull;      // 0 ranks below every real value
+    const unsigned c_mine = hd < cnt ? (unsigned)lc[hd] : (unsigned)INT_MAX;
+    const unsigned mh = __reduce_max_sync(0xffffffffu, (unsigned)(key >> 32));
+    const bool top = (unsigned)(key >> 32) == mh;
+    const unsigned ml = __reduce_max_sync(0xffffffffu, top ? (unsigned)key : 0u);
+    const bool holder = top && (unsigned)key == ml;
+    const unsigned c = __reduce_min_sync(0xffffffffu, holder ? c_mine : (unsigned)INT_MAX);
+    if (hd < cnt && holder && c_mine == c) ++hd;                          // the owner pops its head
+    if (lane == 0) {
+      const unsigned long long wkey = ((unsigned long long)mh << 32) | ml;
+      win_val[j] = wkey == 0ull ? -INFINITY : key_f64(wkey);
+      win_idx[j] = (int)c;
     }
-    if (hd < cnt && lc[hd] == c) ++hd;                                  // the owner pops its head
-    if (lane == 0) { win_val[j] = v; win_idx[j] = c; }
   }
   __syncwarp();
   rb::pdl_trigger();
@@ -1081,8 +1091,9 @@ int beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits, int r
   const bool cta_fits = total <= 1024 * kMaxPerThread && smem <= 200 * 1024;
   // (very wide codebooks would push the per-warp bitmaps past the default 48 KB of dynamic shared memory)
   if (force == 0 && nb <= kWarpNb && d_model % 4 == 0 && kWarpQ * per_warp <= 48 * 1024) {
-    RB_CUDA(rb::launch_pdl(beam_step_warp_kernel, dim3(rb::ceil_div(a.nq, kWarpQ)), dim3(kWarpQ * 32),
-                           kWarpQ * per_warp, stream, a));
+    auto kern = a.tv.words == 8 && a.tv.V == 256 ? beam_step_warp_kernel<8>
+                : (a.tv.words == 32 && a.tv.V == 1024 ? beam_step_warp_kernel<32> : beam_step_warp_kernel<0>);
+    RB_CUDA(rb::launch_pdl(kern, dim3(rb::ceil_div(a.nq, kWarpQ)), dim3(kWarpQ * 32), kWarpQ * per_warp, stream, a));
   } else if (force != 2 && cta_fits && (force == 1 || total <= 256 * 32)) {
     // (beyond 8192 candidates per query the arg-max kernel rescans its 25+ candidates per thread after every
     // winner; the radix select is faster there: beam 100 x V 256 runs 249.5 ms per batch of 128 instead of 258.2)
