@@ -519,11 +519,12 @@ __global__ void __launch_bounds__(kSelThreads) beam_step_select_kernel(const Ste
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kWarpNb = 16;          // beams per query this kernel handles
 constexpr int kWarpQ = 4;            // queries (warps) per CTA
-constexpr int kListLd = kWarpNb + 1; // padded per-lane list stride
-// per warp: list values [32][kListLd] f64 | list indices [32][kListLd] i32 | bs[kWarpNb] f64 | win_val[kWarpNb] f64 |
+// per warp: list values [32][nb + 1] f64 | bs[kWarpNb] f64 | win_val[kWarpNb] f64 | list indices [32][nb + 1] i32 |
 //           win_idx[kWarpNb] | row_max, row_log, thr_ok, thr_pen [kWarpNb] f32 | allow[kWarpNb * words]
-__host__ __device__ constexpr size_t warp_step_smem(int words) {
-  return (32 * kListLd * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4 + 4 + 4) + (size_t)kWarpNb * words * 4 + 15) & ~(size_t)15;
+// (the per-lane lists are sized for the launch's nb, not for kWarpNb: shared memory is what bounds the resident warps)
+__host__ __device__ constexpr size_t warp_step_smem(int words, int nb) {
+  return ((size_t)32 * (nb + 1) * 12 + kWarpNb * (8 + 8 + 4 + 4 + 4 + 4 + 4) + (size_t)kWarpNb * words * 4 + 15) &
+         ~(size_t)15;
 }
 
 template <int WORDS>   // codebook words known at compile time (8: V = 256, 32: V = 1024), 0 = read from the trie view
@@ -538,12 +539,13 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   const int b = a.qlist ? a.qlist[bc] : bc;
 
   extern __shared__ __align__(16) unsigned char wsmem_raw[];
-  unsigned char* base = wsmem_raw + warp * warp_step_smem(words);
+  const int list_ld = nb + 1;                  // padded per-lane list stride
+  unsigned char* base = wsmem_raw + warp * warp_step_smem(words, nb);
   double* list_v = reinterpret_cast<double*>(base);
-  double* bs = list_v + 32 * kListLd;
+  double* bs = list_v + 32 * list_ld;
   double* win_val = bs + kWarpNb;
   int* list_c = reinterpret_cast<int*>(win_val + kWarpNb);
-  int* win_idx = list_c + 32 * kListLd;
+  int* win_idx = list_c + 32 * list_ld;
   float* row_max = reinterpret_cast<float*>(win_idx + kWarpNb);
   float* row_log = row_max + kWarpNb;
   float* thr_ok = row_log + kWarpNb;
@@ -605,8 +607,8 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   // the class: the value of a real candidate), and pass 2 compares x with a per-class fp32 threshold rounded so that
   // x < threshold PROVES value(x) < tau (margin 2^-48 relative, far above the 2^-53 rounding of the three float64
   // operations; NaN / infinite thresholds fail the comparison and send the candidate to the exact evaluation).
-  double* lv = list_v + lane * kListLd;
-  int* lc = list_c + lane * kListLd;
+  double* lv = list_v + lane * list_ld;
+  int* lc = list_c + lane * list_ld;
   int cnt = 0;
   constexpr int kBatch = 8;
   const bool lane_tokens = WORDS ? true : (V & 31) == 0;
@@ -820,19 +822,45 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
     a.token_out[r_new] = vj;
     st_out[r_new] = ns;
   }
-  // token history and KV ancestry of the new beams: lane = position (L <= 32: one row per iteration, no divisions;
-  // longer DocIDs walk the positions in chunks of 32)
-  for (int j = 0; j < nb; ++j) {
-    const int pj_ = __shfl_sync(0xffffffffu, pj, j), vj_ = __shfl_sync(0xffffffffu, vj, j);
-    const int src = b * nb + pj_, dst = b * nb + j;
-    for (int p = lane; p < L; p += 32) {
-      hist_out[dst * L + p] = p < t ? a.hist_old[src * L + p] : (p == t ? vj_ : 0);
-      int anc;
-      if (p < t) anc = a.anc_old[src * L + p];
-      else if (p == t) anc = (a.rpq == 1) ? b : src;
-      else if (p == t + 1) anc = dst;
-      else anc = 0;
-      anc_out[dst * L + p] = anc;
+  // token history and KV ancestry of the new beams: lane = position (L <= 32: one row per beam, no divisions, and the
+  // parents' rows of ALL beams are requested before the first store so that their latencies overlap; longer DocIDs
+  // walk the positions in chunks of 32)
+  if (L <= 32) {
+    int hv[kWarpNb], av[kWarpNb];
+#pragma unroll
+    for (int j = 0; j < kWarpNb; ++j) {
+      const int pj_ = __shfl_sync(0xffffffffu, pj, j & 31);
+      const int src = b * nb + pj_;
+      const bool ld = j < nb && lane < t && lane < L;
+      hv[j] = ld ? a.hist_old[src * L + lane] : 0;
+      av[j] = ld ? a.anc_old[src * L + lane] : 0;
+    }
+#pragma unroll
+    for (int j = 0; j < kWarpNb; ++j) {
+      const int pj_ = __shfl_sync(0xffffffffu, pj, j & 31), vj_ = __shfl_sync(0xffffffffu, vj, j & 31);
+      const int src = b * nb + pj_, dst = b * nb + j;
+      if (j < nb && lane < L) {
+        const int p = lane;
+        int anc = av[j];
+        if (p == t) anc = (a.rpq == 1) ? b : src;
+        else if (p == t + 1) anc = dst;
+        hist_out[dst * L + p] = p == t ? vj_ : hv[j];
+        anc_out[dst * L + p] = anc;
+      }
+    }
+  } else {
+    for (int j = 0; j < nb; ++j) {
+      const int pj_ = __shfl_sync(0xffffffffu, pj, j), vj_ = __shfl_sync(0xffffffffu, vj, j);
+      const int src = b * nb + pj_, dst = b * nb + j;
+      for (int p = lane; p < L; p += 32) {
+        hist_out[dst * L + p] = p < t ? a.hist_old[src * L + p] : (p == t ? vj_ : 0);
+        int anc;
+        if (p < t) anc = a.anc_old[src * L + p];
+        else if (p == t) anc = (a.rpq == 1) ? b : src;
+        else if (p == t + 1) anc = dst;
+        else anc = 0;
+        anc_out[dst * L + p] = anc;
+      }
     }
   }
   if (a.embed_table != nullptr) {                                    // next decoder input rows (d_model % 4 == 0)
@@ -1086,7 +1114,7 @@ int beam_step(rb200_beam* bm, const rb200_trie* trie, const float* logits, int r
   const int64_t total = (int64_t)nb * bm->V;
   const char* fe = getenv("RB200_BEAM");       // cta | select: force one formulation (parity tests); read per call
   const int force = !fe ? 0 : (strcmp(fe, "cta") == 0 ? 1 : (strcmp(fe, "select") == 0 ? 2 : 0));
-  const size_t per_warp = warp_step_smem(a.tv.words);
+  const size_t per_warp = warp_step_smem(a.tv.words, nb);
   const size_t smem = cta_smem_bytes(nb, a.tv.words);
   const bool cta_fits = total <= 1024 * kMaxPerThread && smem <= 200 * 1024;
   // (very wide codebooks would push the per-warp bitmaps past the default 48 KB of dynamic shared memory)
