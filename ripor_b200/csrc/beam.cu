@@ -569,13 +569,15 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
     }
     __syncwarp();
     int code[kWarpNb];                                              // implicit ranges: column t of their <= 32 rows
+    const unsigned implicit = __ballot_sync(0xffffffffu, lane < nb && my.hi - my.lo > 0 && my.node < 0 && t < a.tv.L);
 #pragma unroll
     for (int i = 0; i < kWarpNb; ++i) {
-      const int node_i = __shfl_sync(0xffffffffu, my.node, i & 31);
-      const int lo_i = __shfl_sync(0xffffffffu, my.lo, i & 31);
-      const int n_i = __shfl_sync(0xffffffffu, my.hi - my.lo, i & 31);
-      code[i] = (i < nb && n_i > 0 && node_i < 0 && t < a.tv.L && lane < n_i)
-                    ? rb::trie_code(a.tv, (int64_t)lo_i + lane, t) : -1;
+      code[i] = -1;
+      if ((implicit >> i) & 1u) {                                   // (warp-uniform: only beams on implicit ranges pay)
+        const int lo_i = __shfl_sync(0xffffffffu, my.lo, i);
+        const int n_i = __shfl_sync(0xffffffffu, my.hi - my.lo, i);
+        if (lane < n_i) code[i] = rb::trie_code(a.tv, (int64_t)lo_i + lane, t);
+      }
     }
 #pragma unroll
     for (int i = 0; i < kWarpNb; ++i)
@@ -792,19 +794,24 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
   }
   {                                                                 // implicit ranges: warp-wide count per beam
     int code[kWarpNb];
+    const unsigned implicit = __ballot_sync(0xffffffffu, live && sj.node < 0);
 #pragma unroll
     for (int j = 0; j < kWarpNb; ++j) {
-      const int node_j = __shfl_sync(0xffffffffu, sj.node, j & 31);
-      const int lo_j = __shfl_sync(0xffffffffu, sj.lo, j & 31);
-      const int n_j = __shfl_sync(0xffffffffu, live ? nj : 0, j & 31);
-      code[j] = (j < nb && n_j > 0 && node_j < 0 && lane < n_j) ? rb::trie_code(a.tv, (int64_t)lo_j + lane, t) : INT_MAX;
+      code[j] = INT_MAX;
+      if ((implicit >> j) & 1u) {                                     // (warp-uniform)
+        const int lo_j = __shfl_sync(0xffffffffu, sj.lo, j);
+        const int n_j = __shfl_sync(0xffffffffu, nj, j);
+        if (lane < n_j) code[j] = rb::trie_code(a.tv, (int64_t)lo_j + lane, t);
+      }
     }
 #pragma unroll
     for (int j = 0; j < kWarpNb; ++j) {
-      const int v_j = __shfl_sync(0xffffffffu, vj, j & 31);
-      const int less = __popc(__ballot_sync(0xffffffffu, code[j] < v_j));
-      const int leq = __popc(__ballot_sync(0xffffffffu, code[j] <= v_j));   // INT_MAX never counts (v_j < V)
-      if (lane == j && live && sj.node < 0 && leq != less) ns = TrieState{sj.lo + less, sj.lo + leq, -1, 0};
+      if ((implicit >> j) & 1u) {
+        const int v_j = __shfl_sync(0xffffffffu, vj, j);
+        const int less = __popc(__ballot_sync(0xffffffffu, code[j] < v_j));
+        const int leq = __popc(__ballot_sync(0xffffffffu, code[j] <= v_j));   // INT_MAX never counts (v_j < V)
+        if (lane == j && leq != less) ns = TrieState{sj.lo + less, sj.lo + leq, -1, 0};
+      }
     }
   }
   // every beam on a single leaf: the rest of the query's DocIDs is determined by the trie -> freeze it
@@ -829,17 +836,19 @@ __global__ void __launch_bounds__(kWarpQ * 32) beam_step_warp_kernel(const StepA
     int hv[kWarpNb], av[kWarpNb];
 #pragma unroll
     for (int j = 0; j < kWarpNb; ++j) {
-      const int pj_ = __shfl_sync(0xffffffffu, pj, j & 31);
+      if (j >= nb) break;
+      const int pj_ = __shfl_sync(0xffffffffu, pj, j);
       const int src = b * nb + pj_;
-      const bool ld = j < nb && lane < t && lane < L;
+      const bool ld = lane < t && lane < L;
       hv[j] = ld ? a.hist_old[src * L + lane] : 0;
       av[j] = ld ? a.anc_old[src * L + lane] : 0;
     }
 #pragma unroll
     for (int j = 0; j < kWarpNb; ++j) {
-      const int pj_ = __shfl_sync(0xffffffffu, pj, j & 31), vj_ = __shfl_sync(0xffffffffu, vj, j & 31);
+      if (j >= nb) break;
+      const int pj_ = __shfl_sync(0xffffffffu, pj, j), vj_ = __shfl_sync(0xffffffffu, vj, j);
       const int src = b * nb + pj_, dst = b * nb + j;
-      if (j < nb && lane < L) {
+      if (lane < L) {
         const int p = lane;
         int anc = av[j];
         if (p == t) anc = (a.rpq == 1) ? b : src;
