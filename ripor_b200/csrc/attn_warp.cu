@@ -710,6 +710,42 @@ __device__ __forceinline__ void split_h2(float x, float y, uint32_t& hi, uint32_
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
 
+// 4 x 4 transpose across the lanes of a quad (t4 = lane & 3): lane d ends with r[s] = (lane s's r[d])
+__device__ __forceinline__ void quad_transpose4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, int t4) {
+  const bool odd = t4 & 1, up = t4 & 2;
+  uint32_t x = __shfl_xor_sync(0xffffffffu, odd ? r0 : r1, 1);
+  if (odd) r0 = x; else r1 = x;
+  x = __shfl_xor_sync(0xffffffffu, odd ? r2 : r3, 1);
+  if (odd) r2 = x; else r3 = x;
+  x = __shfl_xor_sync(0xffffffffu, up ? r0 : r2, 2);
+  if (up) r0 = x; else r2 = x;
+  x = __shfl_xor_sync(0xffffffffu, up ? r1 : r3, 2);
+  if (up) r1 = x; else r3 = x;
+}
+
+// One output row of a 16-row m16n8 accumulator tile (64 dims: lane (g, t4) holds columns nd * 8 + 2 * t4, + 1 of the
+// eight dim tiles nd) scaled by inv and written as fp16 hi / lo planes. The pairs are split in registers, transposed
+// across the quad so that lane t4 owns the whole 16-byte chunks nd = t4 and t4 + 4, and stored with four 16-byte
+// stores per row (the generic act_store2 path costs 32 four-byte stores plus a mode switch and a range-check branch
+// per pair: ~30 % of the instructions of the tail attention kernels). Must be called by all 32 lanes; `live` guards
+// only the stores. row_hi = hi plane of the row at the head's first dim, plane = distance to the lo plane.
+__device__ __forceinline__ void store_row_planes_f16(__half* row_hi, int64_t plane, const float (&o)[8][4], int w0,
+                                                     float inv, bool live, int t4, bool& bad) {
+  uint32_t hi[8], lo[8];
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) split_h2(o[nd][w0] * inv, o[nd][w0 + 1] * inv, hi[nd], lo[nd], bad);
+  quad_transpose4(hi[0], hi[1], hi[2], hi[3], t4);
+  quad_transpose4(hi[4], hi[5], hi[6], hi[7], t4);
+  quad_transpose4(lo[0], lo[1], lo[2], lo[3], t4);
+  quad_transpose4(lo[4], lo[5], lo[6], lo[7], t4);
+  if (live) {
+    *reinterpret_cast<uint4*>(row_hi + t4 * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(row_hi + 32 + t4 * 8) = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    *reinterpret_cast<uint4*>(row_hi + plane + t4 * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    *reinterpret_cast<uint4*>(row_hi + plane + 32 + t4 * 8) = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+  }
+}
+
 template <int MINB>   // resident CTAs per SM the register allocation aims at (3: 170 registers, 4: 128)
 __global__ void __launch_bounds__(128, MINB) cross_attn_mma16_kernel(CrossAttnArgs a, ActOut ctx) {
   __shared__ __align__(16) __half k_hi[32 * kKLd], k_lo[32 * kKLd], v_hi[32 * kKLd], v_lo[32 * kKLd];
@@ -760,8 +796,9 @@ __global__ void __launch_bounds__(128, MINB) cross_attn_mma16_kernel(CrossAttnAr
   // gridDim.y CTAs share one (query, head): each restages the <= 32 keys and takes every gridDim.y-th group of 4 tiles
   for (int tile = blockIdx.y * 4 + warp; tile * 16 < nrows; tile += 4 * gridDim.y) {
     const int q0 = tile * 16 + g, q1 = q0 + 8;
-    const float* qr0 = a.q + global_row(min(q0, nrows - 1)) * q_ld + h * 64 + 2 * t;
-    const float* qr1 = a.q + global_row(min(q1, nrows - 1)) * q_ld + h * 64 + 2 * t;
+    const int64_t row0g = global_row(min(q0, nrows - 1)), row1g = global_row(min(q1, nrows - 1));   // (divisions: once)
+    const float* qr0 = a.q + row0g * q_ld + h * 64 + 2 * t;
+    const float* qr1 = a.q + row1g * q_ld + h * 64 + 2 * t;
     float2 qa[4][4];                                                // A fragments (raw fp32 pairs) of the 4 k-steps
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
@@ -846,18 +883,9 @@ __global__ void __launch_bounds__(128, MINB) cross_attn_mma16_kernel(CrossAttnAr
       }
     }
     const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
-    if (q0 < nrows) {
-      const int64_t base = global_row(q0) * inner + h * 64 + 2 * t;
-#pragma unroll
-      for (int nd = 0; nd < 8; ++nd)
-        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
-    }
-    if (q1 < nrows) {
-      const int64_t base = global_row(q1) * inner + h * 64 + 2 * t;
-#pragma unroll
-      for (int nd = 0; nd < 8; ++nd)
-        act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
-    }
+    __half* ctx_hi = static_cast<__half*>(ctx.base) + h * 64;
+    store_row_planes_f16(ctx_hi + row0g * inner, ctx.plane, oacc, 0, inv0, q0 < nrows, t, bad);
+    store_row_planes_f16(ctx_hi + row1g * inner, ctx.plane, oacc, 2, inv1, q1 < nrows, t, bad);
   }
   if (bad && ctx.overflow) *ctx.overflow = 1;
   pdl_trigger();
@@ -920,7 +948,7 @@ __device__ __forceinline__ void tail_load_q_f32(const TailAttnArgs& a, int rp, i
 __device__ __forceinline__ void tail_mma16_tile(const TailAttnArgs& a, const ActOut& ctx, const __half* k_hi,
                                                 const __half* k_lo, const __half* v_hi, const __half* v_lo, int rp,
                                                 int h, int t, int T, int tile, const uint32_t (&qh)[4][4],
-                                                const uint32_t (&ql)[4][4]) {
+                                                const uint32_t (&ql)[4][4], bool& bad) {
   const int lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
@@ -1003,18 +1031,11 @@ __device__ __forceinline__ void tail_mma16_tile(const TailAttnArgs& a, const Act
     }
   }
   const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
-  if (q0 < T) {
-    const int64_t base = ((int64_t)a.lay.off[t + q0] + rp) * inner + h * 64 + 2 * t4;
-#pragma unroll
-    for (int nd = 0; nd < 8; ++nd)
-      act_store2(ctx, base + nd * 8, make_float2(oacc[nd][0] * inv0, oacc[nd][1] * inv0));
-  }
-  if (q1 < T) {
-    const int64_t base = ((int64_t)a.lay.off[t + q1] + rp) * inner + h * 64 + 2 * t4;
-#pragma unroll
-    for (int nd = 0; nd < 8; ++nd)
-      act_store2(ctx, base + nd * 8, make_float2(oacc[nd][2] * inv1, oacc[nd][3] * inv1));
-  }
+  __half* ctx_hi = static_cast<__half*>(ctx.base) + h * 64;
+  store_row_planes_f16(ctx_hi + ((int64_t)a.lay.off[t + min(q0, T - 1)] + rp) * inner, ctx.plane, oacc, 0, inv0, q0 < T,
+                       t4, bad);
+  store_row_planes_f16(ctx_hi + ((int64_t)a.lay.off[t + min(q1, T - 1)] + rp) * inner, ctx.plane, oacc, 2, inv1, q1 < T,
+                       t4, bad);
 }
 
 // all tiles of a task; with planes the next tile's Q words are requested before the current tile computes
@@ -1033,7 +1054,7 @@ __device__ __forceinline__ void tail_mma16_tiles(const TailAttnArgs& a, const Ac
       if (qplanes) tail_load_q_planes(a, rp, h, t, T, tile + 1, qhn, qln);
       else tail_load_q_f32(a, rp, h, t, T, tile + 1, qhn, qln, bad);
     }
-    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, tile, qh, ql);
+    tail_mma16_tile(a, ctx, k_hi, k_lo, v_hi, v_lo, rp, h, t, T, tile, qh, ql, bad);
     if (more) {
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk)
