@@ -686,8 +686,9 @@ __global__ void __launch_bounds__(128, 3) cross_attn_mma_kernel(CrossAttnArgs a,
 // fragments of P V come out of ldmatrix.trans.
 constexpr int kKLd = 72;   // halfs per staged K row (64 dims + pad): conflict-free B fragments
 
+// (not volatile: a pure function of its operands, so independent accumulator chains may be interleaved)
 __device__ __forceinline__ void mma_f16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
@@ -733,7 +734,10 @@ __device__ __forceinline__ void store_row_planes_f16(__half* row_hi, int64_t pla
                                                      float inv, bool live, int t4, bool& bad) {
   uint32_t hi[8], lo[8];
 #pragma unroll
-  for (int nd = 0; nd < 8; ++nd) split_h2(o[nd][w0] * inv, o[nd][w0 + 1] * inv, hi[nd], lo[nd], bad);
+  // (no range check: a row of softmax(S) V is a convex combination of V rows that passed theirs when they were split)
+  bool unchecked = false;
+#pragma unroll
+  for (int nd = 0; nd < 8; ++nd) split_h2(o[nd][w0] * inv, o[nd][w0 + 1] * inv, hi[nd], lo[nd], unchecked);
   quad_transpose4(hi[0], hi[1], hi[2], hi[3], t4);
   quad_transpose4(hi[4], hi[5], hi[6], hi[7], t4);
   quad_transpose4(lo[0], lo[1], lo[2], lo[3], t4);
@@ -787,8 +791,11 @@ __global__ void __launch_bounds__(128, MINB) cross_attn_mma16_kernel(CrossAttnAr
   __syncthreads();
   const int nrows = (a.ragged ? a.lay.P - t0 : a.nblocks) * rpq;
   const int64_t q_ld = a.q_ld ? a.q_ld : inner;
+  // q / rpq by multiplication: exact while q * rpq < 2^32 (q < 32 positions x rpq rows, rpq <= 2048 beams)
+  const uint32_t rpq_magic = (uint32_t)(0x100000000ull / (uint32_t)rpq) + ((0x100000000ull % (uint32_t)rpq) ? 1u : 0u);
   auto global_row = [&](int q) {
-    return (a.ragged ? (int64_t)a.lay.off[t0 + q / rpq] : (int64_t)(q / rpq) * a.block_rows) + (int64_t)b * rpq + (q % rpq);
+    const int blk = rpq == 1 ? q : (int)__umulhi((uint32_t)q, rpq_magic);
+    return (a.ragged ? (int64_t)a.lay.off[t0 + blk] : (int64_t)blk * a.block_rows) + (int64_t)b * rpq + (q - blk * rpq);
   };
   const uint32_t* kh32 = reinterpret_cast<const uint32_t*>(k_hi);
   const uint32_t* kl32 = reinterpret_cast<const uint32_t*>(k_lo);
@@ -818,13 +825,20 @@ __global__ void __launch_bounds__(128, MINB) cross_attn_mma16_kernel(CrossAttnAr
 #pragma unroll
       for (int u = 0; u < 4; ++u) split_h2(qa[kk][u].x, qa[kk][u].y, ah[u], al[u], bad);
 #pragma unroll
+      // term-major over the four key tiles: consecutive MMAs write different accumulators (the three products of
+      // one accumulator issued back to back wait for each other's result); per accumulator the order is unchanged
+      uint32_t bh0[4], bh1[4], bl0[4], bl1[4];
+#pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t;      // words: K[key nt*8+g][dims kk*16 + 2t, +1]
-        const uint32_t bh0 = kh32[o0], bh1 = kh32[o0 + 4], bl0 = kl32[o0], bl1 = kl32[o0 + 4];
-        mma_f16(sacc[nt], al, bh0, bh1);
-        mma_f16(sacc[nt], ah, bl0, bl1);
-        mma_f16(sacc[nt], ah, bh0, bh1);
+        bh0[nt] = kh32[o0]; bh1[nt] = kh32[o0 + 4]; bl0[nt] = kl32[o0]; bl1[nt] = kl32[o0 + 4];
       }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_f16(sacc[nt], al, bh0[nt], bh1[nt]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_f16(sacc[nt], ah, bl0[nt], bl1[nt]);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) mma_f16(sacc[nt], ah, bh0[nt], bh1[nt]);
     }
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
@@ -870,16 +884,19 @@ __global__ void __launch_bounds__(128, MINB) cross_attn_mma16_kernel(CrossAttnAr
       split_h2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ph[2], pl[2], nb_);
       split_h2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ph[3], pl[3], nb_);
 #pragma unroll
-      for (int nd = 0; nd < 8; nd += 2) {
-        uint32_t bh[4], bl[4];                                     // b0, b1 of dim tiles nd and nd + 1
-        ldmatrix_x4_trans(bh, v_hi + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
-        ldmatrix_x4_trans(bl, v_lo + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
-        mma_f16(oacc[nd], pl, bh[0], bh[1]);
-        mma_f16(oacc[nd], ph, bl[0], bl[1]);
-        mma_f16(oacc[nd], ph, bh[0], bh[1]);
-        mma_f16(oacc[nd + 1], pl, bh[2], bh[3]);
-        mma_f16(oacc[nd + 1], ph, bl[2], bl[3]);
-        mma_f16(oacc[nd + 1], ph, bh[2], bh[3]);
+      for (int nd = 0; nd < 8; nd += 4) {                        // four dim tiles at a time, term-major
+        uint32_t bh[2][4], bl[2][4];                               // [pair][b0, b1 of dim tile 2*pair, b0, b1 of the next]
+#pragma unroll
+        for (int pr = 0; pr < 2; ++pr) {
+          ldmatrix_x4_trans(bh[pr], v_hi + (ks * 16 + vrow) * kKLd + (nd + 2 * pr) * 8 + vcol);
+          ldmatrix_x4_trans(bl[pr], v_lo + (ks * 16 + vrow) * kKLd + (nd + 2 * pr) * 8 + vcol);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_f16(oacc[nd + j], pl, bh[j >> 1][2 * (j & 1)], bh[j >> 1][2 * (j & 1) + 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_f16(oacc[nd + j], ph, bl[j >> 1][2 * (j & 1)], bl[j >> 1][2 * (j & 1) + 1]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) mma_f16(oacc[nd + j], ph, bh[j >> 1][2 * (j & 1)], bh[j >> 1][2 * (j & 1) + 1]);
       }
     }
     const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
@@ -964,13 +981,19 @@ __device__ __forceinline__ void tail_mma16_tile(const TailAttnArgs& a, const Act
 #pragma unroll
   for (int kk = 0; kk < 4; ++kk) {
 #pragma unroll
+    // term-major over the four key tiles (see cross_attn_mma16_kernel): independent accumulators back to back
+    uint32_t bh0[4], bh1[4], bl0[4], bl1[4];
+#pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
       const int o0 = (nt * 8 + g) * (kKLd / 2) + kk * 8 + t4;
-      const uint32_t bh0 = kh32[o0], bh1 = kh32[o0 + 4], bl0 = kl32[o0], bl1 = kl32[o0 + 4];
-      mma_f16(sacc[nt], ql[kk], bh0, bh1);
-      mma_f16(sacc[nt], qh[kk], bl0, bl1);
-      mma_f16(sacc[nt], qh[kk], bh0, bh1);
+      bh0[nt] = kh32[o0]; bh1[nt] = kh32[o0 + 4]; bl0[nt] = kl32[o0]; bl1[nt] = kl32[o0 + 4];
     }
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_f16(sacc[nt], ql[kk], bh0[nt], bh1[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_f16(sacc[nt], qh[kk], bl0[nt], bl1[nt]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) mma_f16(sacc[nt], qh[kk], bh0[nt], bh1[nt]);
   }
   // causal mask + relative position bias: row q sits at position t + q and sees keys p <= t + q
   const int pq0 = t + q0, pq1 = t + q1;
@@ -1018,16 +1041,19 @@ __device__ __forceinline__ void tail_mma16_tile(const TailAttnArgs& a, const Act
     split_h2(sacc[2 * ks + 1][0], sacc[2 * ks + 1][1], ph[2], pl[2], nb_);
     split_h2(sacc[2 * ks + 1][2], sacc[2 * ks + 1][3], ph[3], pl[3], nb_);
 #pragma unroll
-    for (int nd = 0; nd < 8; nd += 2) {
-      uint32_t bh[4], bl[4];
-      ldmatrix_x4_trans(bh, v_hi + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
-      ldmatrix_x4_trans(bl, v_lo + (ks * 16 + vrow) * kKLd + nd * 8 + vcol);
-      mma_f16(oacc[nd], pl, bh[0], bh[1]);
-      mma_f16(oacc[nd], ph, bl[0], bl[1]);
-      mma_f16(oacc[nd], ph, bh[0], bh[1]);
-      mma_f16(oacc[nd + 1], pl, bh[2], bh[3]);
-      mma_f16(oacc[nd + 1], ph, bl[2], bl[3]);
-      mma_f16(oacc[nd + 1], ph, bh[2], bh[3]);
+    for (int nd = 0; nd < 8; nd += 4) {                          // four dim tiles at a time, term-major
+      uint32_t bh[2][4], bl[2][4];
+#pragma unroll
+      for (int pr = 0; pr < 2; ++pr) {
+        ldmatrix_x4_trans(bh[pr], v_hi + (ks * 16 + vrow) * kKLd + (nd + 2 * pr) * 8 + vcol);
+        ldmatrix_x4_trans(bl[pr], v_lo + (ks * 16 + vrow) * kKLd + (nd + 2 * pr) * 8 + vcol);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_f16(oacc[nd + j], pl, bh[j >> 1][2 * (j & 1)], bh[j >> 1][2 * (j & 1) + 1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_f16(oacc[nd + j], ph, bl[j >> 1][2 * (j & 1)], bl[j >> 1][2 * (j & 1) + 1]);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) mma_f16(oacc[nd + j], ph, bh[j >> 1][2 * (j & 1)], bh[j >> 1][2 * (j & 1) + 1]);
     }
   }
   const float inv0 = sum0 > 0.f ? 1.0f / sum0 : 0.f, inv1 = sum1 > 0.f ? 1.0f / sum1 : 0.f;
