@@ -65,6 +65,40 @@ for prec in precisions:
     assert torch.isfinite(out["scores"]).all()
     print(f"ok forward {prec}", flush=True)
 lib = _lib.lib()
+# the warp beam-step kernel in its compile-time codebook widths (V = 256, 1024) and the generic one (V = 64), alone,
+# against the all-float64 CTA kernel: random logits, a few steps each
+import ctypes as C  # noqa: E402
+
+
+def beam_steps(trie, B, nb, Lb, Vb, logits):
+    h = C.c_void_p()
+    _lib.check(lib.rb200_beam_create(0, B, nb, Lb, Vb, C.byref(h)))
+    _lib.check(lib.rb200_beam_reset(h, trie.handle, B, _lib.stream_ptr()))
+    for t in range(Lb):
+        lg = logits[t][: B] if t == 0 else logits[t]
+        _lib.check(lib.rb200_beam_step(h, trie.handle, lg.data_ptr(), 1 if t == 0 else nb, 0, None, None, 0,
+                                       _lib.stream_ptr()))
+    seqs = torch.empty((B * nb, Lb + 1), dtype=torch.int64, device=dev)
+    sc = torch.empty((B * nb,), dtype=torch.float32, device=dev)
+    leaf = torch.empty((B * nb, 2), dtype=torch.int32, device=dev)
+    _lib.check(lib.rb200_beam_finalize(h, trie.handle, nb, 1.0, seqs.data_ptr(), sc.data_ptr(), leaf.data_ptr(),
+                                       _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    lib.rb200_beam_free(h)
+    return seqs.cpu(), sc.cpu(), leaf.cpu()
+
+
+for Vb, nb in ((256, 10), (1024, 7), (64, 16)):
+    Lb, B = 4, 5
+    tr = DocidTrie.from_codes(syn.make_codes(4000, Lb, Vb, seed=3, dup_frac=0.05), Vb).upload(0)
+    g = torch.Generator().manual_seed(Vb)
+    logits = [(torch.randn(B * nb, Vb, generator=g) * 3).to(dev) for _ in range(Lb)]
+    got = beam_steps(tr, B, nb, Lb, Vb, logits)
+    os.environ["RB200_BEAM"] = "cta"
+    want = beam_steps(tr, B, nb, Lb, Vb, logits)
+    os.environ.pop("RB200_BEAM")
+    assert all(torch.equal(x, y) for x, y in zip(got, want)), (Vb, nb)
+    print(f"ok beam warp kernel V={Vb} nb={nb}", flush=True)
 for prec in precisions:
     for M, N, K in ((1, 64, 64), (77, 136, 72)):
         A, W = torch.randn(M, K, device=dev), torch.randn(N, K, device=dev)
