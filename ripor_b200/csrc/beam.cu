@@ -163,11 +163,19 @@ __device__ __forceinline__ void cta_write_back(const StepArgs& a, int b, const d
     anc_out[dst * L + p] = anc;
   }
   if (a.embed_table != nullptr) {
+    // next decoder input rows: one warp per new beam, 16-byte copies (no per-element divisions: with 1000 beams the
+    // element-wise version was ~30 % of this kernel, which runs on ONE SM per query)
     const int d = a.d_model;
-    for (int e = tid; e < nb * d; e += THREADS) {
-      const int j = e / d, col = e - j * d;
+    for (int j = warp; j < nb; j += NW) {
       const int v = win_idx[j] % V;
-      a.next_x[(int64_t)(b * nb + j) * d + col] = a.embed_table[(int64_t)v * d + col];
+      const float* src = a.embed_table + (int64_t)v * d;
+      float* dst = a.next_x + (int64_t)(b * nb + j) * d;
+      if ((d & 3) == 0) {
+        for (int c = lane; c < (d >> 2); c += 32)
+          reinterpret_cast<float4*>(dst)[c] = reinterpret_cast<const float4*>(src)[c];
+      } else {
+        for (int c = lane; c < d; c += 32) dst[c] = src[c];
+      }
     }
   }
 }
@@ -374,10 +382,10 @@ __global__ void __launch_bounds__(kSelThreads) beam_step_select_kernel(const Ste
   cta_prepare<kSelThreads>(a, b, bc, bs, allow, row_max, row_log);
 
   // walk this thread's candidates c = tid + k * THREADS as (beam i, token v) without divisions
+  const int step_i = kSelThreads / V, step_v = kSelThreads - step_i * V;
   auto for_each_cand = [&](auto&& fn) {
     constexpr int kBatch = 4;                  // logits of kBatch candidates in flight before any is consumed
-    int i = 0, v = tid;
-    while (v >= V) { v -= V; ++i; }
+    int i = tid / V, v = tid - i * V;
     for (int c0 = tid; c0 < total; c0 += kSelThreads * kBatch) {
       float xs[kBatch];
       int is[kBatch], vs[kBatch];
@@ -385,8 +393,9 @@ __global__ void __launch_bounds__(kSelThreads) beam_step_select_kernel(const Ste
       for (int u = 0; u < kBatch; ++u) {
         is[u] = i; vs[u] = v;
         xs[u] = (c0 + kSelThreads * u < total) ? a.logits[(int64_t)(bc * a.rpq + (a.rpq == 1 ? 0 : i)) * V + v] : 0.f;
-        v += kSelThreads;
-        while (v >= V) { v -= V; ++i; }
+        i += step_i;                           // c += kSelThreads without a division or a subtract loop
+        v += step_v;
+        if (v >= V) { v -= V; ++i; }
       }
 #pragma unroll
       for (int u = 0; u < kBatch; ++u) {
@@ -1007,27 +1016,64 @@ __global__ void tail_pick_kernel(rb::TailLayout lay, int nb, int L, int V, int a
 // One CTA per frozen query: replay its remaining steps. At each step the candidate of the beam in slot j is
 // (score_j + x, flat index j * V + token) and the beams are re-ranked by (value desc, flat index asc), exactly what
 // the step kernels do when every beam has a single valid child (all other candidates carry the -1e9 penalty).
-__global__ void tail_finish_kernel(rb::TailLayout lay, int nb, int L, int V, const int32_t* __restrict__ fz_list,
+__global__ void tail_finish_kernel(rb::TailLayout lay, int nb, int L, int V, int n2,
+                                   const int32_t* __restrict__ fz_list,
                                    const int32_t* __restrict__ qstate, const float* __restrict__ picked,
                                    const double* __restrict__ sc_fz, const TrieState* __restrict__ st_fz,
                                    const int32_t* __restrict__ hist_fz, double* __restrict__ sc_out,
                                    TrieState* __restrict__ st_out, int32_t* __restrict__ hist_out) {
+  // n2 = 0: rank counting (nb^2 compares per step, fine for a few dozen beams); n2 = nb rounded up to a power of two:
+  // bitonic sort of (value desc, slot asc) per step - with 1000 beams 27 steps x 10^6 float64 compares on one SM took
+  // 0.8 ms, the sorting network does the same re-ranking in 55 compare-exchange rounds per step
   extern __shared__ __align__(16) unsigned char tf_raw[];
+  const int cap = n2 > 0 ? n2 : nb;
   double* s = reinterpret_cast<double*>(tf_raw);       // [nb] score of the beam in slot j
-  double* val = s + nb;                                // [nb]
-  int* perm = reinterpret_cast<int*>(val + nb);        // [nb] frozen beam index in slot j
-  int* nperm = perm + nb;                              // [nb]
+  double* val = s + cap;                               // [cap]
+  int* perm = reinterpret_cast<int*>(val + cap);       // [nb] frozen beam index in slot j
+  int* nperm = perm + cap;                             // [cap]: new order (rank counting) / slot of a sorted entry
   const int fq = blockIdx.x;
   const int b = fz_list[fq];
   const int t0 = qstate[b];
   for (int j = threadIdx.x; j < nb; j += blockDim.x) { s[j] = sc_fz[b * nb + j]; perm[j] = j; }
   __syncthreads();
   for (int p = t0; p < lay.P; ++p) {
-    for (int j = threadIdx.x; j < nb; j += blockDim.x) {
-      const double v = (double)picked[lay.off[p] + fq * nb + perm[j]] + s[j];
-      val[j] = v == v ? v : kNanRank;
+    for (int j = threadIdx.x; j < cap; j += blockDim.x) {
+      if (j < nb) {
+        const double v = (double)picked[lay.off[p] + fq * nb + perm[j]] + s[j];
+        val[j] = v == v ? v : kNanRank;
+      } else {
+        val[j] = -INFINITY;                              // padding of the sorting network: behind every real entry
+      }
+      if (n2 > 0) nperm[j] = j;
     }
     __syncthreads();
+    if (n2 > 0) {
+      // (value desc, slot asc); slot = position before this step = flat index order among equal values
+      for (int k = 2; k <= n2; k <<= 1) {
+        for (int jj = k >> 1; jj > 0; jj >>= 1) {
+          for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+            const int q = i ^ jj;
+            if (q > i) {
+              const double vi = val[i], vq = val[q];
+              const int si = nperm[i], sq = nperm[q];
+              const bool i_first = vi > vq || (vi == vq && si < sq);
+              const bool up = (i & k) == 0;
+              if (up ? !i_first : i_first) {
+                val[i] = vq; val[q] = vi;
+                nperm[i] = sq; nperm[q] = si;
+              }
+            }
+          }
+          __syncthreads();
+        }
+      }
+      int mine_perm = 0;
+      for (int j = threadIdx.x; j < nb; j += blockDim.x) mine_perm = perm[nperm[j]];     // (nb <= blockDim.x on this path)
+      __syncthreads();
+      for (int j = threadIdx.x; j < nb; j += blockDim.x) { s[j] = val[j]; perm[j] = mine_perm; }
+      __syncthreads();
+      continue;
+    }
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
       const double mine = val[j];
       // candidates ahead of slot j's under (value desc, flat index asc); flat index = slot * V + token with
@@ -1209,14 +1255,25 @@ int launch_tail_finish(rb200_beam* bm, const rb200_trie* trie, const TailLayout&
   const int c = bm->cur;
   int threads = ((nb + 31) / 32) * 32;
   threads = threads > 1024 ? 1024 : threads;
+  // sorting network instead of rank counting for wide beams that fit one entry per thread (RB200_TAIL_SORT=0 | 1 forces)
+  int n2 = 0;
+  {
+    const char* e = getenv("RB200_TAIL_SORT");
+    const bool want = e ? e[0] == '1' : nb > 64;
+    if (want && nb <= 1024) {
+      n2 = 2;
+      while (n2 < nb) n2 <<= 1;
+    }
+  }
   static bool attr_set = false;
   if (!attr_set) {
     RB_CUDA(cudaFuncSetAttribute(tail_finish_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSelMaxNb * 24));
     attr_set = true;
   }
-  tail_finish_kernel<<<nfz, threads, (size_t)nb * 24, s>>>(lay, nb, bm->L, bm->V, bm->fz_list, bm->qstate, picked,
-                                                          bm->fz_scores, bm->fz_state, bm->fz_hist, bm->scores[c],
-                                                          bm->state[c], bm->hist[c]);
+  const int cap = n2 > 0 ? n2 : nb;
+  tail_finish_kernel<<<nfz, threads, (size_t)cap * 24, s>>>(lay, nb, bm->L, bm->V, n2, bm->fz_list, bm->qstate, picked,
+                                                           bm->fz_scores, bm->fz_state, bm->fz_hist, bm->scores[c],
+                                                           bm->state[c], bm->hist[c]);
   RB_CUDA(cudaGetLastError());
   launch_count()++;
   return 0;

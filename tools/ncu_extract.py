@@ -43,7 +43,10 @@ def main(path):
                 if "byte" in u:
                     d[name] = to_bytes(r[idx[k]], u)
                 else:
-                    v = float(r[idx[k]].replace(",", ""))
+                    try:
+                        v = float(r[idx[k]].replace(",", ""))
+                    except ValueError:               # "no data" for a counter this capture did not collect
+                        continue
                     if name == "us":
                         v = v / 1e3 if u in ("ns", "nsecond") else v
                     d[name] = v
