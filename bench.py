@@ -382,18 +382,23 @@ def run_ours(a):
             hb = C.c_void_p()
             _lib.check(lib.rb200_beam_create(local, Rq, nb, L, a.codebook, C.byref(hb)))
             big = torch.randn((Rq * nb, a.codebook), device=dev)
-            _lib.check(lib.rb200_beam_reset(hb, trie.handle, Rq, _lib.stream_ptr()))
-            _lib.check(lib.rb200_beam_step(hb, trie.handle, big.data_ptr(), 1, 0, None, None, 0, _lib.stream_ptr()))
             b0, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             nlaunch = min(4, L - 1)
-            torch.cuda.synchronize()
-            b0.record()
-            for _ in range(nlaunch):
-                _lib.check(lib.rb200_beam_step(hb, trie.handle, big.data_ptr(), nb, 0, None, None, 0, _lib.stream_ptr()))
-            b1.record()
-            torch.cuda.synchronize()
+            reps, total_ms = 4, 0.0                                  # repetition 0 is the warm-up (cold trie tables)
+            for rep in range(reps):
+                _lib.check(lib.rb200_beam_reset(hb, trie.handle, Rq, _lib.stream_ptr()))
+                _lib.check(lib.rb200_beam_step(hb, trie.handle, big.data_ptr(), 1, 0, None, None, 0, _lib.stream_ptr()))
+                torch.cuda.synchronize()
+                b0.record()
+                for _ in range(nlaunch):                             # steps 1..4: 168 MB of logits per launch (> L2)
+                    _lib.check(lib.rb200_beam_step(hb, trie.handle, big.data_ptr(), nb, 0, None, None, 0,
+                                                   _lib.stream_ptr()))
+                b1.record()
+                torch.cuda.synchronize()
+                if rep > 0:
+                    total_ms += b0.elapsed_time(b1)
             lib.rb200_beam_free(hb)
-            us = b0.elapsed_time(b1) * 1e3 / nlaunch
+            us = total_ms * 1e3 / (nlaunch * (reps - 1))
             per_row = a.codebook * 4 + (8 + 16) + (8 + 16 + 4 + 4) + 2 * L * 4 * 2   # logits, score+state in, out, hist+anc in/out
             nbytes = Rq * nb * per_row
             survey_bytes = Rq * nb * (a.codebook * 4 + a.codebook // 8 + 8 + 4 + 8 + 20)   # ~1.07 KB per beam-step
@@ -403,9 +408,10 @@ def run_ours(a):
                          "algorithmic_bytes_per_launch": nbytes, "achieved_gbs": nbytes / us / 1e3, "peak_gbs": hbm,
                          "frac": nbytes / us / 1e3 / hbm, "bound": "hbm",
                          "survey_8d_bytes_per_launch": survey_bytes, "survey_8d_frac": survey_bytes / us / 1e3 / hbm,
-                         "note": "float64 candidate ranking over nb*V logits per query, trie child lookup (dependent "
-                                 "random reads into 338 MB of trie tables), history / ancestry reorder; one warp per "
-                                 "query; latency-bound, < 1 % of a search"}
+                         "note": "one warp per query: fp32 pre-filter against proven per-beam thresholds, float64 "
+                                 "ranking of the survivors, trie child lookup (dependent random reads into 338 MB of "
+                                 "trie tables), history / ancestry reorder; issue-bound (ncu: 64 % issue slots busy), "
+                                 "< 0.5 % of a search; 3 timed repetitions of steps 1..4 after one warm-up repetition"}
             del big
         except Exception as exc:                                     # the secondary figure must never break the bench line
             trie_topk = {"error": str(exc)[:200]}
