@@ -310,10 +310,11 @@ static int engine_build(rb200_engine* e, const rb200_engine_config* cfg) {
   RB_TRY(dev_alloc(e, (void**)&e->dec_final_ln, d * 4));
   {
     const char* f = getenv("RB200_FOLD");
-    // Opt-in (RB200_FOLD=1): parity-green on B200, but the row-per-lane reads/writes of the old residual values in
-    // the EPI_RESID_NORM epilogue cost as much as the 36 RMSNorm launches they replace (2550 vs 2610 q/s at the
-    // bench shape); it needs a second staging tile per epilogue warp (TMA loads of C) to pay off.
-    e->fold = e->mode != RB200_PREC_FP32 && d % 64 == 0 && (f && f[0] == '1');
+    // NormFold (default; RB200_FOLD=0 turns it off): the T5 layer norms live in the epilogues of the GEMMs around
+    // them instead of 3 RMSNorm launches per layer. It pays since the new residual values leave the epilogue as TMA
+    // stores (58.1 -> 56.6 ms per batch at the bench shape); with row-per-lane 16-byte stores it cost as much as the
+    // RMSNorm launches it replaced.
+    e->fold = e->mode != RB200_PREC_FP32 && d % 64 == 0 && !(f && f[0] == '0');
     e->np = d / 64;
   }
   {

@@ -401,7 +401,6 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
           for (int hc = 0; hc < 2; ++hc) {
             uint32_t r[32];
             tmem_ld32(taddr + (uint32_t)(c + hc * 32), r);
-            float* xdst = const_cast<float*>(xrow) + col0 + c + hc * 32;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               const float v0 = fmaf(__uint_as_float(r[4 * j + 0]), out_scale, xo[hc][j].x);
@@ -411,11 +410,11 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               ssq += v0 * v0 + v1 * v1 + v2 * v2 + v3 * v3;
               xn[hc][4 * j + 0] = __float_as_uint(v0); xn[hc][4 * j + 1] = __float_as_uint(v1);
               xn[hc][4 * j + 2] = __float_as_uint(v2); xn[hc][4 * j + 3] = __float_as_uint(v3);
-              // the new residual row goes straight back from registers (fire-and-forget 16-byte stores; L2 merges
-              // them), which keeps the single staging tile free for the two plane tiles below
-              if (myrow < M && col0 + c + hc * 32 + 4 * j < N)
-                *reinterpret_cast<float4*>(xdst + 4 * j) = make_float4(v0, v1, v2, v3);
             }
+            // the new residual values leave through the staging tile as one TMA store per 32 columns (row-per-lane
+            // 16-byte stores touch 32 rows per instruction: the same scattered-store pattern that held the tail
+            // attention kernels back)
+            if (rows_live && col0 + c + hc * 32 < N) emit_tile(tile_s, lane, xn[hc], &tmO0, col0 + c + hc * 32, row0, false);
           }
           if (myrow < M && col0 + c < N) nf.ss_out[(int64_t)myrow * nf.np + ((col0 + c) >> 6)] = ssq;
           // operand planes of x / r_prev for the next GEMM

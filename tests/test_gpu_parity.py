@@ -217,9 +217,12 @@ def test_search_matches_golden_from_literal_reference(name, precision):
             assert abs(run[q][k] - gold[str(q)][k]) < 1e-3 * c["L"]
 
 
-@pytest.mark.parametrize("precision", ["fp32", "tf32x3", "fp16x3", "bf16x3"])
-def test_t5base_search_matches_cached_oracle(precision):
-    """t5-base, 100k-doc trie, L=32, beam=10: DocIDs exact, scores within 1e-3 (north-star tolerances)."""
+@pytest.mark.parametrize("precision,fold", [("fp32", "1"), ("tf32x3", "1"), ("fp16x3", "1"), ("bf16x3", "1"),
+                                            ("tf32x3", "0"), ("fp16x3", "0")])
+def test_t5base_search_matches_cached_oracle(monkeypatch, precision, fold):
+    """t5-base, 100k-doc trie, L=32, beam=10: DocIDs exact, scores within 1e-3 (north-star tolerances). fold = 1 is
+    the default engine (layer norms inside the GEMM epilogues), fold = 0 the separate RMSNorm launches."""
+    monkeypatch.setenv("RB200_FOLD", fold)
     L, nb, B, V = 32, 10, 6, 256
     dims = syn.T5Dims.t5_base(docid_len=L)
     w = syn.make_weights(dims)
@@ -251,8 +254,12 @@ def test_fast_modes_run_and_stay_close():
         assert torch.allclose(top, ref_sc.view(B, nb)[:, 0], atol=tol), precision
 
 
-def test_fp16x3_overflow_is_loud():
-    """fp16x3 cannot represent |x| > 65504: the engine must return NaN scores, never silently wrong DocIDs."""
+@pytest.mark.parametrize("fold", ["0", "1"])
+def test_fp16x3_overflow_is_loud(monkeypatch, fold):
+    """fp16x3 cannot represent |x| > 65504: the engine must return NaN scores (or refuse the weights), never silently
+    wrong DocIDs. fold = 0: separate RMSNorm launches, the layer-norm gain acts on the activations; fold = 1 (the
+    default): the gain is folded into the packed wi matrix, which then no longer fits the fp16 planes."""
+    monkeypatch.setenv("RB200_FOLD", fold)
     dims = syn.T5Dims.tiny()
     w = syn.make_weights(dims)
     w = dict(w)
@@ -264,11 +271,15 @@ def test_fp16x3_overflow_is_loud():
     ids, mask = syn.make_queries(2, S=12, vocab_size=dims.vocab_size)
     model = T5SeqAQEncoder.from_weights(dims, w)
     trie = DocidTrie.from_codes(codes, dims.decoder_vocab_size)
-    out = _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="fp16x3")
-    assert torch.isnan(out.sequences_scores).all()
+    if fold == "0":
+        out = _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="fp16x3")
+        assert torch.isnan(out.sequences_scores).all()
+    else:
+        with pytest.raises(ValueError, match="fp16 range"):      # gain x wi does not fit the fp16 planes: refused
+            _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="fp16x3")
     out = _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="tf32x3")
     assert not torch.isnan(out.sequences_scores).any()
-    # precision="auto" starts in fp16x3, sees the poisoned scores and redoes the batch in tf32x3
+    # precision="auto" starts in fp16x3, sees the poisoned scores (or the refusal) and redoes the batch in tf32x3
     auto = _engine_search(model, trie, ids, mask, 4, dims.docid_len, precision="auto")
     assert auto.precision == "tf32x3" and model.base_model.fp16_ok is False
     assert torch.equal(auto.sequences, out.sequences) and torch.equal(auto.sequences_scores, out.sequences_scores)
