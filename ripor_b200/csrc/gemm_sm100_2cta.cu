@@ -393,10 +393,6 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         for (int c = 0; c < HALF; c += 64) {
           uint32_t xn[2][32];
           float ssq = 0.f;
-          if (c > 0) {
-            load_x(col0 + c, xo[0]);
-            load_x(col0 + c + 32, xo[1]);
-          }
 #pragma unroll
           for (int hc = 0; hc < 2; ++hc) {
             uint32_t r[32];
@@ -411,6 +407,9 @@ gemm_sm100_2cta_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
               xn[hc][4 * j + 0] = __float_as_uint(v0); xn[hc][4 * j + 1] = __float_as_uint(v1);
               xn[hc][4 * j + 2] = __float_as_uint(v2); xn[hc][4 * j + 3] = __float_as_uint(v3);
             }
+            // this slot's old values are consumed: request the same 32 columns of the next 64-column chunk now, so
+            // that they arrive while the tile stores and the plane conversion of this chunk run
+            if (c + 64 < HALF) load_x(col0 + c + 64 + hc * 32, xo[hc]);
             // the new residual values leave through the staging tile as one TMA store per 32 columns (row-per-lane
             // 16-byte stores touch 32 rows per instruction: the same scattered-store pattern that held the tail
             // attention kernels back)
