@@ -368,7 +368,11 @@ def run_ours(a):
                 "issued_mma_tflops": achieved * mma_mult,
                 "note": "achieved = algorithmic 2*M*N*K of every GEMM launch of one step / their summed event time; "
                         f"{prec} issues {mma_mult} tensor-core MMA(s) per algorithmic product, so frac <= 1/{mma_mult} "
-                        "by construction; frac_of_split_peak = issued / peak",
+                        "by construction; frac_of_split_peak = issued / peak. The GEMM launches include the T5 "
+                        "layer norms (NormFold, default): the residual add, the sum of squares and the next GEMM's "
+                        "normalised operand planes run in the o / co / wo epilogues instead of 3 RMSNorm launches per "
+                        "layer, which lengthens those launches (lower GEMM-only frac) and shortens the step (higher "
+                        "step_level_frac); RB200_FOLD=0 restores the separate launches",
                 "frac_of_split_peak": achieved * mma_mult / peak,
                 # whole step, per GPU: SURVEY 8d's 70.5 GFLOP per query x queries/s / peak
                 "step_level_frac": 70.5e9 * B / (main["ms_per_step"] / 1e3) / 1e12 / peak
