@@ -137,7 +137,7 @@ __device__ __forceinline__ void cp_async16_on(float* dst_smem, const float* src)
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d32), "l"(src) : "memory");
 }
 
-__global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArgs a, ActOut ctx, int pcap) {
+__global__ void __launch_bounds__(kWarps * 32, 7) self_attn_smem_kernel(SelfAttnArgs a, ActOut ctx, int pcap) {
   extern __shared__ __align__(16) float ssmem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int half = lane >> 4, l16 = lane & 15;
@@ -151,10 +151,22 @@ __global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArg
   pdl_wait();
   // persistent: a few resident CTAs per SM walk the (row, head) tasks (7680 four-warp CTAs cost more in block
   // scheduling than the short early steps take to compute)
-  for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += gridDim.x * kWarps) {
+  // The original row id and the lineage's cache slots of a task come out of two dependent loads (compaction list ->
+  // ancestry table) that the K/V requests depend on in turn: they are fetched one task ahead.
+  const int stride = gridDim.x * kWarps;
+  auto task_rows = [&](int wid, int& orow, int& slot0) {
+    const int m = wid / a.H;
+    orow = orig_row(a, m);
+    const int arow = (a.rpq == 1) ? orow * a.nb : orow;
+    slot0 = lane < t ? lane * (int)a.row_cap + a.anc[(int64_t)arow * L + lane] : -1;     // positions 0..31 (chunk 0)
+  };
+  int orow_n = 0, slot0_n = -1;
+  if ((int)(blockIdx.x * kWarps + warp) < ntask) task_rows(blockIdx.x * kWarps + warp, orow_n, slot0_n);
+  for (int wid = blockIdx.x * kWarps + warp; wid < ntask; wid += stride) {
   const int m = wid / a.H, h = wid - m * a.H;
-  const int orow = orig_row(a, m);
+  const int orow = orow_n, slot0 = slot0_n;
   const int arow = (a.rpq == 1) ? orow * a.nb : orow;
+  if (wid + stride < ntask) task_rows(wid + stride, orow_n, slot0_n);
   const float* qrow = a.qkv + (int64_t)m * 3 * inner + h * 64;     // q | k | v of this row at position t
   __syncwarp();                                                     // the previous task's readers are done
   if (lane < 16) cp_async16_on(qs + lane * 4, qrow + lane * 4);
@@ -167,7 +179,8 @@ __global__ void __launch_bounds__(kWarps * 32) self_attn_smem_kernel(SelfAttnArg
     if (c0 > 0) __syncwarp();
     // ---- stage: lane p owns the cache slot of position c0 + p; 16 lanes x 16 B per row, 2 rows per instruction --
     const int pl = c0 + lane;
-    const int slot_l = pl < t ? pl * (int)a.row_cap + a.anc[(int64_t)arow * L + pl] : -1;   // -1: position t (qkv)
+    const int slot_l = c0 == 0 ? slot0
+                               : (pl < t ? pl * (int)a.row_cap + a.anc[(int64_t)arow * L + pl] : -1);   // -1: position t (qkv)
     const int nr = (np + 1) >> 1;
 #pragma unroll 4
     for (int r = 0; r < nr; ++r) {
