@@ -853,6 +853,22 @@ __global__ void __launch_bounds__(128, MINB) cross_attn_mma16_kernel(CrossAttnAr
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) mma_f16(sacc[nt], ah, bh0[nt], bh1[nt]);
     }
+    if (a.rel_bias != nullptr) {
+      // encoder self-attention through this kernel (the S rows of a sequence are the "beams" of its query slot):
+      // relative position bias rel_bias[h][(key - query position) + rel_S - 1] on the score fragments
+      const float* rb = a.rel_bias + (int64_t)h * (2 * a.rel_S - 1) + (a.rel_S - 1);
+      const int c0 = min(q0, nrows - 1), c1 = min(q1, nrows - 1);
+      const int p0 = c0 - (rpq == 1 ? c0 : (int)__umulhi((uint32_t)c0, rpq_magic)) * rpq;     // position in the sequence
+      const int p1 = c1 - (rpq == 1 ? c1 : (int)__umulhi((uint32_t)c1, rpq_magic)) * rpq;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int w = 0; w < 2; ++w) {
+          const int key = min(nt * 8 + 2 * t + w, S - 1);
+          sacc[nt][w] += __ldg(rb + (key - p0));
+          sacc[nt][2 + w] += __ldg(rb + (key - p1));
+        }
+    }
     float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt)
@@ -1296,8 +1312,19 @@ bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, 
   }();
   // many rows per (query, head) against <= 32 keys (the forced tail): tensor-core kernel
   // (the exact fp32 mode keeps the FFMA kernel)
-  if (use_mma && ctx.mode != 0 && a.S <= 32 && a.rel_bias == nullptr &&
-      (a.ragged || (int64_t)a.nblocks * a.rows_per_query >= 32)) {
+  // (the fp16 kernel also takes the encoder's self-attention: relative position bias on its score fragments;
+  // RB200_ENC_MMA=0 keeps the encoder on the FFMA kernel)
+  static const bool enc_mma = []() {
+    const char* e = getenv("RB200_ENC_MMA");
+    return !(e && e[0] == '0');
+  }();
+  const bool bias_ok = a.rel_bias == nullptr || (enc_mma && prec_is_fp16(ctx.mode) && a.rel_S >= a.S);
+  static const int min_rows = []() {               // rows per (query, head) from which the tensor-core kernel is used
+    const char* e = getenv("RB200_XATTN_MINROWS");
+    return e && atoi(e) > 0 ? atoi(e) : 32;
+  }();
+  if (use_mma && ctx.mode != 0 && a.S <= 32 && bias_ok &&
+      (a.ragged || (int64_t)a.nblocks * a.rows_per_query >= min_rows)) {
     const int B = a.M / a.rows_per_query;
     // resident CTAs per SM the registers are budgeted for: 4 (128 registers, no spills) measured 212 us per tail
     // launch against 233 us at 3 (157 registers; 5 with 96 registers and a few spills: 208 us); RB200_XATTN_OCC=3

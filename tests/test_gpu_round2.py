@@ -242,6 +242,35 @@ def test_forced_tail_replay_equals_real_steps(monkeypatch, rerank, integer_logit
 
 
 # ------------------------------------------------------------------------------------------------
+# encoder self-attention on the tensor-core attention kernel (S = 32: relative position bias on the score fragments)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("enc_mma", ["1", "0"])
+def test_encoder_states_at_source_length_32(monkeypatch, enc_mma):
+    """With 32 source positions the fp16x3 engine runs the encoder's bidirectional self-attention through the
+    tensor-core kernel of the forced tail (relative position bias added to the score fragments, padded keys masked);
+    RB200_ENC_MMA=0 keeps it on the FFMA kernel. Both: encoder states == the oracle's T5 encoder, ragged masks."""
+    monkeypatch.setenv("RB200_ENC_MMA", enc_mma)
+    L, nb, B, S = 6, 4, 7, 32
+    dims = syn.T5Dims.tiny(docid_len=L)
+    w = syn.make_weights(dims)
+    codes = syn.make_codes(500, L, dims.decoder_vocab_size)
+    ids, mask = syn.make_queries(B, S=S, vocab_size=dims.vocab_size, min_len=3)
+    assert mask.sum(1).min() < S                          # at least one padded sequence
+    model = T5SeqAQEncoder.from_weights(dims, w)
+    trie = DocidTrie.from_codes(codes, dims.decoder_vocab_size)
+    out = _engine_search(model, trie, ids, mask, nb, L, precision="fp16x3")
+    eng = model.base_model.get_engine(B, nb, S, "fp16x3")
+    p = C.c_void_p()
+    _lib.check(_lib.lib().rb200_engine_encoder_states(eng.h, C.byref(p)))
+    enc = _copy_from_device(p.value, B * S * dims.d_model * 4, np.float32).reshape(B, S, -1)
+    ref = t5_math.encoder_forward(w, dims, ids.long(), mask.long()).numpy()
+    m = mask.numpy().astype(bool)
+    assert np.abs(enc[m] - ref[m]).max() < 2e-4
+    ref_seq, ref_sc, _, _ = helpers.oracle_cached_search(w, dims, codes, ids, mask, nb, L)
+    assert helpers.compare_ranked(out.sequences, out.sequences_scores, ref_seq, ref_sc, nb, atol=1e-3) == 0
+
+
+# ------------------------------------------------------------------------------------------------
 # engine: queries freeze at different steps (skewed trie), shapes change between calls
 # ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("precision", ["fp32", "fp16x3", "tf32x3"])
