@@ -1314,10 +1314,8 @@ bool launch_cross_attn_warp(const CrossAttnArgs& a, ActOut ctx, cudaStream_t s, 
   // (the exact fp32 mode keeps the FFMA kernel)
   // (the fp16 kernel also takes the encoder's self-attention: relative position bias on its score fragments;
   // RB200_ENC_MMA=0 keeps the encoder on the FFMA kernel)
-  static const bool enc_mma = []() {
-    const char* e = getenv("RB200_ENC_MMA");
-    return !(e && e[0] == '0');
-  }();
+  const char* enc_env = a.rel_bias != nullptr ? getenv("RB200_ENC_MMA") : nullptr;   // read per call (parity tests)
+  const bool enc_mma = !(enc_env && enc_env[0] == '0');
   const bool bias_ok = a.rel_bias == nullptr || (enc_mma && prec_is_fp16(ctx.mode) && a.rel_S >= a.S);
   static const int min_rows = []() {               // rows per (query, head) from which the tensor-core kernel is used
     const char* e = getenv("RB200_XATTN_MINROWS");
