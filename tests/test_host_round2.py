@@ -255,3 +255,77 @@ def test_mrr_matches_truncate_run_plus_trec_eval_semantics():
     # truncation happens BEFORE the tie-break: with k=1 the stable sort keeps "a" (inserted first)
     assert ev.mrr_k({"q1": {"a": 2.0, "b": 2.0}}, {"q1": {"b": 1}}, 1) == 0.0
     assert ev.mrr_k({}, qrel, 10) == 0.0
+
+
+# ------------------------------------------------------------------------------------------------
+# the fp32 pre-filter of the warp beam kernel (csrc/beam.cu): the threshold rule, restated in numpy
+# ------------------------------------------------------------------------------------------------
+def _f32_round_down(v):
+    """float64 -> the largest float32 <= v (what __double2float_rd returns)."""
+    with np.errstate(over="ignore"):
+        f = np.float32(v)
+    if np.isnan(f):
+        return f
+    if np.float64(f) > v:
+        f = np.nextafter(f, np.float32(-np.inf))
+    return f
+
+
+def _thresholds(tau, bs):
+    with np.errstate(invalid="ignore", over="ignore"):
+        dlt = np.float64(tau) - np.float64(bs)
+        mag = abs(np.float64(tau)) + abs(np.float64(bs))
+        t_ok = _f32_round_down(dlt - mag * 2.0 ** -48)
+        t_pen = _f32_round_down((dlt + 1e9) - (mag + 1e9) * 2.0 ** -47)
+    return t_ok, t_pen
+
+
+def _value(x, ok, bs):
+    with np.errstate(invalid="ignore", over="ignore"):
+        processed = np.float64(x) if ok else np.float64(x) + np.float64(-1e9)
+        val = processed + np.float64(bs)
+    return val if val == val else -1.7976931348623157e308
+
+
+def test_beam_prefilter_threshold_rule_never_drops_a_candidate():
+    """beam_step_warp_kernel skips a candidate when its fp32 logit x is below a per-(beam, class) threshold. The rule
+    must be one-sided: x < threshold implies value(x) < tau in the kernel's float64 arithmetic, for every tau and beam
+    score (also across the 1e9 penalty, at exact ties and next to the threshold itself); non-finite thresholds must
+    fail the comparison. Exhaustive neighbourhood walk around the threshold for seeded (tau, score) pairs."""
+    rng = np.random.default_rng(0)
+    scales = [1e-30, 1e-6, 1.0, 37.5, 1e4, 1e9, 3e9, 1e15, 1e30]
+    cases = [(0.0, 0.0), (0.0, -1e9), (-1e9, 0.0), (5.0, 5.0), (-2e9, -1e9), (1.0, -3.0)]
+    for _ in range(400):
+        s1, s2 = rng.choice(scales, 2)
+        cases.append((float(rng.standard_normal() * s1), float(rng.standard_normal() * s2)))
+    for v in (np.inf, -np.inf, np.nan, 1.7e308, -1.7976931348623157e308):
+        cases.append((v, 1.0))
+    checked = 0
+    for tau, bs in cases:
+        t_ok, t_pen = _thresholds(tau, bs)
+        for ok, thr in ((True, t_ok), (False, t_pen)):
+            if not np.isfinite(thr):
+                # -inf / NaN / +inf thresholds: `x < thr` is false for every finite x below them only if thr is -inf or
+                # NaN; a +inf threshold may only arise when no finite x can reach tau
+                if thr == np.inf:
+                    assert _value(np.finfo(np.float32).max, ok, bs) < tau
+                continue
+            x = np.float32(thr)
+            for _step in range(64):                       # the 64 floats just below the threshold are all skipped ...
+                x = np.nextafter(x, np.float32(-np.inf))
+                assert _value(x, ok, bs) < tau, (tau, bs, ok, float(x))
+                checked += 1
+            for x in (np.float32(thr) - np.float32(abs(float(thr)) * 0.5 + 1.0), np.float32(-3.0e38)):
+                if x < thr:
+                    assert _value(x, ok, bs) < tau
+            # ... and the margin is small: a logit four margins above tau - score (rounded up to fp32) reaches tau
+            if abs(tau) < 1e30 and abs(bs) < 1e30:
+                mag = abs(np.float64(tau)) + abs(np.float64(bs))
+                up = (np.float64(tau) - np.float64(bs)) + 4 * mag * 2.0 ** -48 if ok else \
+                    (np.float64(tau) - np.float64(bs) + 1e9) + 4 * (mag + 1e9) * 2.0 ** -47
+                xr = np.float32(up)
+                if np.float64(xr) < up:
+                    xr = np.nextafter(xr, np.float32(np.inf))
+                if np.isfinite(xr):
+                    assert not (xr < thr) and _value(xr, ok, bs) >= tau, (tau, bs, ok)
+    assert checked > 20000
